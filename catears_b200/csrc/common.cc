@@ -1,0 +1,151 @@
+// common.cc -- error state, device selection and workspace buffers of libce_gpu.so.
+#include "common.h"
+
+#include <string.h>
+
+namespace ce {
+
+namespace {
+thread_local char g_error[2048] = "";
+thread_local int64_t g_launches = 0;
+}  // namespace
+
+void SetError(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+const char *LastError() { return g_error; }
+void ClearError() { g_error[0] = '\0'; }
+int64_t &LaunchCounter() { return g_launches; }
+
+int DeviceCount() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int UseDevice(int device) {
+  int n = DeviceCount();
+  if (n <= 0) {
+    SetError("no CUDA device is visible: libce_gpu has no CPU fallback");
+    return CE_GPU_ENODEVICE;
+  }
+  if (device < 0 || device >= n) {
+    SetError("device %d out of range (%d visible)", device, n);
+    return CE_GPU_ENODEVICE;
+  }
+  static thread_local int checked_major[64] = {0};
+  CE_CUDA(cudaSetDevice(device));
+  if (device < 64 && checked_major[device] == 0) {
+    int major = 0;
+    CE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    checked_major[device] = major;
+  }
+  if (device < 64 && checked_major[device] != 10) {
+    SetError("device %d has compute capability %d.x; libce_gpu is built for sm_100a only", device,
+             checked_major[device]);
+    return CE_GPU_ENODEVICE;
+  }
+  return CE_GPU_OK;
+}
+
+bool IsDevicePtr(const void *p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int DevBuf::Reserve(size_t bytes) {
+  if (bytes <= cap) return CE_GPU_OK;
+  Free();
+  size_t want = (bytes + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ptr = nullptr;
+    SetError("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    return CE_GPU_ENOMEM;
+  }
+  cap = want;
+  return CE_GPU_OK;
+}
+
+void DevBuf::Free() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+int PinnedBuf::Acquire(size_t bytes) {
+  if (pending) {
+    CE_CUDA(cudaEventSynchronize(inflight));
+    pending = false;
+  }
+  if (bytes <= cap) return CE_GPU_OK;
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = (bytes + 4095) & ~(size_t)4095;
+  cudaError_t e = cudaMallocHost(&ptr, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ptr = nullptr;
+    SetError("cudaMallocHost(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    return CE_GPU_ENOMEM;
+  }
+  cap = want;
+  return CE_GPU_OK;
+}
+
+int PinnedBuf::Release(cudaStream_t s) {
+  if (!inflight) CE_CUDA(cudaEventCreateWithFlags(&inflight, cudaEventDisableTiming));
+  CE_CUDA(cudaEventRecord(inflight, s));
+  pending = true;
+  return CE_GPU_OK;
+}
+
+void PinnedBuf::Free() {
+  if (pending) cudaEventSynchronize(inflight);
+  pending = false;
+  if (inflight) cudaEventDestroy(inflight);
+  inflight = nullptr;
+  if (ptr) cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+int Table::Upload(size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return CE_GPU_OK;
+  CE_CUDA(cudaMemcpyAsync(dev_buf.ptr, host_buf.ptr, bytes, cudaMemcpyHostToDevice, s));
+  return host_buf.Release(s);
+}
+
+int StageIn(const void *src, size_t bytes, DevBuf *stage, cudaStream_t s, const void **dev_out) {
+  if (bytes == 0 || IsDevicePtr(src)) {
+    *dev_out = src;
+    return CE_GPU_OK;
+  }
+  CE_CHECK(stage->Reserve(bytes));
+  CE_CUDA(cudaMemcpyAsync(stage->ptr, src, bytes, cudaMemcpyHostToDevice, s));
+  *dev_out = stage->ptr;
+  return CE_GPU_OK;
+}
+
+int StageOut(void *dst, const void *dev_src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return CE_GPU_OK;
+  CE_CUDA(cudaMemcpyAsync(dst, dev_src, bytes, cudaMemcpyDeviceToHost, s));
+  CE_CUDA(cudaStreamSynchronize(s));
+  return CE_GPU_OK;
+}
+
+}  // namespace ce

@@ -1,0 +1,580 @@
+// gemm.cu -- K3/K4: the Linear layers of the acoustic model as tcgen05 tensor-core GEMMs.
+//
+// Replaces, fused in one kernel per layer,
+//   SpliceLayer + NarrowLayer   src/nnet.cc:50-75,182-202   (implicit: one K-slab per tap, the
+//                                                            same activation rows at a row offset)
+//   LinearLayer                 src/nnet.cc:22-36 -> MatMat src/matrix.cc:300-323 (cblas_sgemm)
+//   Quantize'd variant          MatMat_U8U8F32 src/matrix.cc:389-420 -> gemmlowp
+//                               eight_bit_int_gemm.cc:107-141,383-391, internal/unpack.h:118-125
+//   bias / ReLU / BatchNorm     src/nnet.cc:34,149-160,106-117
+//   FindMinMax of the result    src/matrix.cc:329-345 (input of the next layer's Quantize)
+//
+// Structure (Blackwell-native): persistent CTAs, one per SM, 6 warps:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of A [128 rows x 128 B]
+//               and B [256 rows x 128 B] into a 4-stage shared-memory ring, mbarrier-signalled;
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (cta_group::1, M=128, N=256,
+//               K = 32 bytes per instruction) with the accumulator in tensor memory;
+//               two 256-column accumulator stages so tile i+1 is multiplied while tile i drains;
+//   warps 2-5   epilogue: tcgen05.ld of the accumulator (one TMEM lane quadrant per warp),
+//               the exact fp32 chain of the reference (un-fused multiplies/adds, its order),
+//               transpose through shared memory, coalesced 128-byte row stores.
+// Data paths: kind::i8 (u8 x u8 -> s32, the zero-point algebra of gemmlowp applied to the exact
+// raw sums), kind::f16 (bf16 -> fp32) and kind::tf32 (optionally three passes hi*hi + hi*lo +
+// lo*hi for fp32-class accuracy).
+
+#include "gemm.h"
+
+#include <cuda_runtime.h>
+#include <float.h>
+
+#include <mutex>
+
+namespace ce {
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB
+constexpr int kBBytes = kTileN * kTileKBytes;            // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kStagePitch = 36;                          // floats per staged row (32 + 4 pad)
+constexpr int kEpiStageBytes = 32 * kStagePitch * 4;     // per epilogue warp
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes +
+                           kEpiWarps * kEpiStageBytes + 256 /*barriers*/;
+constexpr int kTmemCols = 512;
+constexpr int kAccStages = 2;
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                       uint32_t idesc, uint32_t accumulate) {
+  if (KIND == kKindI8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if (KIND == kKindBF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// 32 lanes x 32 columns of 32-bit accumulators: thread i gets lane (base + i), v[j] = column j.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes,
+// 8-row groups 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                                // leading byte offset (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset
+  d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+  return d;
+}
+
+template <int KIND>
+__device__ __forceinline__ uint32_t make_idesc() {
+  const uint32_t c_fmt = (KIND == kKindI8) ? 2u : 1u;                 // S32 : F32
+  const uint32_t ab_fmt = (KIND == kKindI8) ? 0u : (KIND == kKindBF16) ? 1u : 2u;   // U8, BF16, TF32
+  return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
+            const GemmArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char *smem_a = smem;                                   // [kStages][kABytes]
+  unsigned char *smem_b = smem + kStages * kABytes;               // [kStages][kBBytes]
+  float *epi_stage = reinterpret_cast<float *>(smem + kStages * kStageBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + kEpiWarps * kEpiStageBytes);
+  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = smem_u32(bars + kStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kStages);
+  const uint32_t bar_tempty = smem_u32(bars + 2 * kStages + kAccStages);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + kTileM - 1) / kTileM;
+  const int n_tiles = (p.N + kTileN - 1) / kTileN;
+  const int total_tiles = m_tiles * n_tiles;
+  constexpr int kEltBytes = (KIND == kKindI8) ? 1 : (KIND == kKindBF16) ? 2 : 4;
+  constexpr int kTileK = kTileKBytes / kEltBytes;
+  const int kb_per_tap = p.c_pad / kTileK;
+  const int steps_per_pass = p.n_taps * kb_per_tap;
+  const int n_steps = p.n_pass * steps_per_pass;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kTileM;
+        const int n0 = (tile % n_tiles) * kTileN;
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+          const CUtensorMap *ma = p.pass_a[ps] ? &map_a1 : &map_a0;
+          const CUtensorMap *mb = p.pass_b[ps] ? &map_b1 : &map_b0;
+          for (int tap = 0; tap < p.n_taps; ++tap) {
+            const int row = m0 + p.tap_off[tap];
+            for (int kb = 0; kb < kb_per_tap; ++kb) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+              tma_load_2d(smem_u32(smem_a + stage * kABytes), ma, bar_full + 8 * stage, kb * kTileK, row);
+              tma_load_2d(smem_u32(smem_b + stage * kBBytes), mb, bar_full + 8 * stage,
+                          tap * p.c_pad + kb * kTileK, n0);
+              if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc<KIND>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileN);
+        for (int step = 0; step < n_steps; ++step) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t da = make_desc(smem_u32(smem_a + stage * kABytes));
+          const uint64_t db = make_desc(smem_u32(smem_b + stage * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kTileKBytes / 32; ++k) {
+            // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+            tc_mma<KIND>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (step | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar_empty + 8 * stage);              // frees the smem slot when the MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(bar_tfull + 8 * acc);                  // accumulator complete
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
+    float *stg = epi_stage + (warp - 2) * (32 * kStagePitch);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / n_tiles;
+      const int m0 = m_tile * kTileM;
+      const int n0 = (tile % n_tiles) * kTileN;
+      const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
+
+      // ---- per-tile / per-row constants ----
+      const int utt = p.tile_utt ? p.tile_utt[m_tile] : 0;
+      int32_t zp_a = 0;
+      float c_scale = 1.0f;
+      int32_t row_corr = 0;                              // zp_b * sum_k A[row][k]
+      int32_t kzz = 0;
+      if (KIND == kKindI8) {
+        const QParam q = p.qa[utt];
+        zp_a = q.zero_point;
+        c_scale = __fmul_rn(q.scale, p.scale_b);         // matrix.cc:403 (float * float)
+        int32_t rs = 0;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int r = my_row + p.tap_off[t];
+          if (r >= 0 && r < p.M) rs += p.a_rowsum[r];
+        }
+        row_corr = p.zp_b * rs;
+        kzz = p.k_true * zp_a * p.zp_b;
+      }
+      bool use_row = false;                              // takes part in the fused FindMinMax
+      if (p.minmax) {
+        int pos = my_row, P = p.M;
+        if (p.utts) {
+          const UttRows ur = p.utts[utt];
+          pos = my_row - ur.row_off;
+          P = ur.rows;
+        }
+        if (pos >= p.mm_lo && pos < P - p.mm_hi) {
+          if (p.next_n_taps == 0) {
+            use_row = true;
+          } else {
+            for (int t = 0; t < p.next_n_taps; ++t) {
+              const int o = pos - p.next_tap_off[t];
+              if (o >= p.next_lo && o < P - p.next_hi) use_row = true;
+            }
+          }
+        }
+      }
+      float vmin = FLT_MAX, vmax = -FLT_MAX;
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
+
+      for (int c = 0; c < kTileN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.n_store) break;                    // warp-uniform
+        uint32_t raw[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), raw);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float x;
+          if (KIND == kKindI8) {
+            // acc = sum (A - zpA)(B - zpB) = raw - zpB*rowsum(A) - zpA*colsum(B) + K*zpA*zpB
+            const int32_t a = (int32_t)raw[j] - row_corr - zp_a * __ldg(p.b_colsum + col) + kzz;
+            if (p.out_acc && my_row < p.M && col < p.N) p.out_acc[(int64_t)my_row * p.ld_out + col] = a;
+            x = __fmul_rn(__int2float_rn(a), c_scale);   // eight_bit_int_gemm.cc:389
+          } else {
+            x = __uint_as_float(raw[j]);
+          }
+          if (p.bias) x = __fadd_rn(x, __ldg(p.bias + col));                       // nnet.cc:34
+          if (p.relu) x = (x < 0.0f) ? 0.0f : x;                                     // nnet.cc:156
+          if (p.bn_scale) {
+            x = __fmul_rn(x, __ldg(p.bn_scale + col));                               // nnet.cc:114
+            x = __fadd_rn(x, __ldg(p.bn_offset + col));                              // nnet.cc:115
+          }
+          if (col >= p.N) x = 0.0f;                      // K padding of the next layer
+          if (use_row && col < p.N) {
+            vmin = (x < vmin) ? x : vmin;                // comparisons as matrix.cc:337-340
+            vmax = (x > vmax) ? x : vmax;
+          }
+          v[j] = x;
+        }
+        // ---- transpose through shared memory: thread = row  ->  8 lanes = one 128-byte row ----
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<float4 *>(stg + lane * kStagePitch + 4 * j) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+        const int sub = lane >> 3;                       // row within a group of 4
+        const int cc = (lane & 7) * 4;                   // column within the 32-wide chunk
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub;
+          const int grow = m0 + quad * 32 + r;
+          const int gcol = col0 + cc;
+          const float4 f = *reinterpret_cast<const float4 *>(stg + r * kStagePitch + cc);
+          if (grow < p.M && gcol < p.n_store) {
+            const int64_t o = (int64_t)grow * p.ld_out + gcol;
+            const bool full = gcol + 4 <= p.n_store;
+            const float e[4] = {f.x, f.y, f.z, f.w};
+            if (p.out_bf16) {
+              if (full) {
+                __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
+                __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&lo2);
+                pk.y = *reinterpret_cast<uint32_t *>(&hi2);
+                *reinterpret_cast<uint2 *>(p.out_bf16 + o) = pk;
+              } else {
+                for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_bf16[o + q] = __float2bfloat16_rn(e[q]);
+              }
+            }
+            if (p.out_f32) {
+              float h[4] = {e[0], e[1], e[2], e[3]};
+              if (p.round_tf32) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) h[q] = round_tf32(e[q]);
+              }
+              if (full) {
+                *reinterpret_cast<float4 *>(p.out_f32 + o) = make_float4(h[0], h[1], h[2], h[3]);
+              } else {
+                for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_f32[o + q] = h[q];
+              }
+              if (p.out_lo) {
+                if (full) {
+                  *reinterpret_cast<float4 *>(p.out_lo + o) =
+                      make_float4(e[0] - h[0], e[1] - h[1], e[2] - h[2], e[3] - h[3]);
+                } else {
+                  for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_lo[o + q] = e[q] - h[q];
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+
+      if (p.minmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+          vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        if (lane == 0 && vmin <= vmax) {
+          atomicMin(p.minmax + 2 * utt, OrderedFromFloat(vmin));
+          atomicMax(p.minmax + 2 * utt + 1, OrderedFromFloat(vmax));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int GetEncodeFn(EncodeTiledFn *out) {
+  static std::mutex mu;
+  static EncodeTiledFn fn = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+      SetError("cuTensorMapEncodeTiled is not available from the driver");
+      return CE_GPU_ECUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  *out = fn;
+  return CE_GPU_OK;
+}
+
+// 2-D map over a row-major [rows x cols] matrix, box = [box_rows x 128 bytes], 128B swizzle.
+int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows, CUtensorMap *map) {
+  EncodeTiledFn fn;
+  CE_CHECK(GetEncodeFn(&fn));
+  const int elt = KindEltBytes(kind);
+  const CUtensorMapDataType dt = kind == kKindI8     ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                 : kind == kKindBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * elt) % 16 != 0) {
+    SetError("GEMM operand is not 16-byte aligned (base %p, row pitch %lld bytes)", base,
+             (long long)(cols * elt));
+    return CE_GPU_EINVAL;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(cols * elt)};
+  cuuint32_t box[2] = {(cuuint32_t)(kTileKBytes / elt), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    SetError("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld kind %d)", (int)r,
+             (long long)rows, (long long)cols, kind);
+    return CE_GPU_ECUDA;
+  }
+  return CE_GPU_OK;
+}
+
+template <int KIND>
+int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
+  CUtensorMap ma0, ma1, mb0, mb1;
+  CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
+  CE_CHECK(MakeMap(KIND, ops.a[1] ? ops.a[1] : ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma1));
+  CE_CHECK(MakeMap(KIND, ops.b[0], ops.rows_b, ops.k_total, kTileN, &mb0));
+  CE_CHECK(MakeMap(KIND, ops.b[1] ? ops.b[1] : ops.b[0], ops.rows_b, ops.k_total, kTileN, &mb1));
+  static thread_local bool configured[64] = {false};
+  int dev = 0;
+  CE_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured[dev] = true;
+  }
+  static thread_local int sm_count[64] = {0};
+  if (dev < 64 && sm_count[dev] == 0) {
+    CE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int m_tiles = (args.M + kTileM - 1) / kTileM;
+  const int n_tiles = (args.N + kTileN - 1) / kTileN;
+  const int64_t tiles = (int64_t)m_tiles * n_tiles;
+  if (tiles <= 0) return CE_GPU_OK;
+  const int sms = dev < 64 ? sm_count[dev] : 148;
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+  gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma0, ma1, mb0, mb1, args);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+}  // namespace
+
+int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
+  if (args.c_pad <= 0 || args.c_pad % KindTileK(kind) != 0 || args.n_taps < 1 ||
+      args.n_taps > kMaxTaps || args.n_pass < 1 || args.n_pass > 3) {
+    SetError("GemmLaunch: bad geometry (c_pad %d, taps %d, passes %d)", args.c_pad, args.n_taps,
+             args.n_pass);
+    return CE_GPU_EINVAL;
+  }
+  if (args.n_store < args.N || args.n_store > args.ld_out) {
+    SetError("GemmLaunch: n_store %d outside [N %d, ld_out %lld]", args.n_store, args.N,
+             (long long)args.ld_out);
+    return CE_GPU_EINVAL;
+  }
+  if (args.ld_out % 4 != 0) {
+    SetError("GemmLaunch: output row stride %lld is not a multiple of 4", (long long)args.ld_out);
+    return CE_GPU_EINVAL;
+  }
+  switch (kind) {
+    case kKindI8: return LaunchKind<kKindI8>(ops, args, s);
+    case kKindBF16: return LaunchKind<kKindBF16>(ops, args, s);
+    case kKindTF32: return LaunchKind<kKindTF32>(ops, args, s);
+  }
+  SetError("GemmLaunch: unknown kind %d", kind);
+  return CE_GPU_EINVAL;
+}
+
+}  // namespace ce

@@ -1,0 +1,116 @@
+// gemm.h -- the tcgen05 implicit-GEMM of the acoustic model's Linear layers (K3/K4).
+#ifndef CE_GPU_GEMM_H_
+#define CE_GPU_GEMM_H_
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace ce {
+
+enum GemmKind { kKindI8 = 0, kKindBF16 = 1, kKindTF32 = 2 };
+
+constexpr int kTileM = 128;          // rows per CTA tile = UMMA M (cta_group::1)
+constexpr int kTileN = 256;          // columns per CTA tile = UMMA N
+constexpr int kTileKBytes = 128;     // one 128-byte swizzle atom of K per pipeline stage
+constexpr int kMaxTaps = 8;
+
+inline int KindEltBytes(int kind) { return kind == kKindI8 ? 1 : kind == kKindBF16 ? 2 : 4; }
+inline int KindTileK(int kind) { return kTileKBytes / KindEltBytes(kind); }   // elements
+
+// Per-utterance affine u8 quantisation parameters (struct QuantizationParams, src/matrix.h:231-234).
+struct QParam {
+  float scale;
+  int32_t zero_point;
+};
+
+// Geometry of one utterance inside the activation row space.  Every utterance owns a block of
+// rows starting at a multiple of kTileM, so that a GEMM tile never spans two utterances.
+struct UttRows {
+  int32_t row_off;   // first row of the block
+  int32_t rows;      // P = T + left_context + right_context
+};
+
+// Device-side arguments of one GEMM launch.  A is an activation matrix [M x c_pad] (row-major,
+// K contiguous); the B operand is the packed weight matrix [N x (n_taps * c_pad)] (K contiguous).
+//   out[m][n] = epilogue( sum_{pass} sum_{tap} sum_{c} A_pass[m + tap_off[tap]][c] *
+//                                                       B_pass[n][tap * c_pad + c] )
+// Rows outside [0, M) read as zero (TMA out-of-bounds fill).
+struct GemmArgs {
+  int32_t M, N;
+  int32_t c_pad;                 // multiple of KindTileK(kind)
+  int32_t n_taps;
+  int32_t tap_off[kMaxTaps];
+  int32_t n_pass;                // 1, or 3 for the error-compensated 3xTF32 product
+  int32_t pass_a[3], pass_b[3];  // operand selectors (0 = hi / only, 1 = lo)
+
+  // ---- epilogue ----
+  const float *bias;             // [N padded to kTileN], nullptr = none          nnet.cc:34
+  const float *bn_scale;         // nullptr = no BatchNorm                        nnet.cc:114
+  const float *bn_offset;        //                                               nnet.cc:115
+  int32_t relu;                  //                                               nnet.cc:156
+  // u8 x u8 -> s32 (gemmlowp contract)
+  const int32_t *a_rowsum;       // [M] sum of the u8 codes of every A row (one tap)
+  const int32_t *b_colsum;       // [N padded] sum over K of the u8 weight codes
+  int32_t zp_b;
+  float scale_b;
+  int32_t k_true;                // un-padded K = n_taps * C
+  const QParam *qa;              // [n_utts] activation quantisation of each utterance
+  const int32_t *tile_utt;       // [ceil(M / kTileM)] utterance of each row tile; nullptr = 0
+  const UttRows *utts;           // [n_utts]; nullptr = one block of M rows
+
+  // outputs (any may be nullptr)
+  float *out_f32;                // fp32 result (for 3xTF32 consumers: the tf32-rounded "hi" part)
+  float *out_lo;                 // v - hi
+  __nv_bfloat16 *out_bf16;
+  int32_t *out_acc;              // int32 accumulators after the zero-point corrections
+  int64_t ld_out;                // row stride (elements) of out_f32 / out_lo / out_bf16 / out_acc
+  int32_t n_store;               // columns written per row (>= N; columns [N, n_store) get 0) --
+                                 // the zero padding of the next layer's K dimension
+  int32_t round_tf32;            // out_f32 = tf32-rounded value (so that out_lo is exact)
+
+  // fused FindMinMax (src/matrix.cc:329-345) for the next layer's Quantize: only rows the next
+  // layer's Splice+Narrow actually reads take part.
+  uint32_t *minmax;              // [n_utts][2] order-preserving encodings; nullptr = off
+  int32_t mm_lo, mm_hi;          // this layer's valid rows of an utterance: [mm_lo, P - mm_hi)
+  int32_t next_n_taps;           // 0: every valid row is used
+  int32_t next_tap_off[kMaxTaps];
+  int32_t next_lo, next_hi;      // next layer's valid output rows: [next_lo, P - next_hi)
+};
+
+struct GemmOperands {            // host-side description for the tensor maps
+  const void *a[2];              // device pointers (hi, lo), [rows_a x c_pad]
+  int64_t rows_a;
+  const void *b[2];              // [n_rows_b x k_total]
+  int64_t rows_b;                // N (rows beyond it read as zero)
+  int64_t k_total;               // n_taps * c_pad
+};
+
+// Enqueues the GEMM.  `kind` selects the tensor-core data path.
+int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args, cudaStream_t s);
+
+// Order-preserving float <-> uint32 map used by the min/max atomics.
+__host__ __device__ inline uint32_t OrderedFromFloat(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f);
+#else
+  uint32_t b;
+  memcpy(&b, &f, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float FloatFromOrdered(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+
+}  // namespace ce
+
+#endif  // CE_GPU_GEMM_H_

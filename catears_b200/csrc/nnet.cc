@@ -1,0 +1,437 @@
+// nnet.cc -- AcousticModel on the device: weight packing at load, and the batched forward pass.
+//
+// Replaces AcousticModel::Read (src/am.cc:26-64), ComputeBatch (src/am.cc:82-113) and
+// Nnet::Propagate (src/nnet.cc:295-307) for whole utterances evaluated as one batch each
+// (chunked and whole-utterance evaluation are the same function).
+//
+// Row space: utterance u of a chunk owns rows [row_off[u], row_off[u] + P_u) with
+// P_u = T_u + left + right and row_off[u] a multiple of 128, in EVERY layer's activation
+// matrix (rows are never compacted).  After block b the rows [cum_left_b, P_u - cum_right_b)
+// are the reference's rows; the others hold values that no valid row ever reads.
+#include "nnet.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+ce_gpu_model::~ce_gpu_model() {
+  cudaSetDevice(device);
+  for (auto &b : blocks) {
+    b.w[0].Free(); b.w[1].Free(); b.bias.Free(); b.bn_scale.Free(); b.bn_offset.Free(); b.colsum.Free();
+  }
+  log_prior.Free(); cmvn_dev.Free();
+  stage_pcm.Free(); stage_feats.Free(); stage_loglik.Free(); stage_argmax.Free();
+  feats.Free(); x0.Free();
+  for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
+  act_u8.Free(); rowsum.Free(); logits.Free(); acc_dump.Free(); minmax.Free(); qparams.Free();
+  fbank_chunks.Free(); cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
+  if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+namespace ce {
+namespace {
+
+inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+uint16_t Bf16Bits(float f) {                              // round to nearest even
+  uint32_t b;
+  memcpy(&b, &f, 4);
+  if ((b & 0x7f800000u) == 0x7f800000u) return (uint16_t)(b >> 16);
+  b += 0x7fffu + ((b >> 16) & 1u);
+  return (uint16_t)(b >> 16);
+}
+
+float Tf32Round(float f) {                                // cvt.rna.tf32.f32
+  uint32_t b;
+  memcpy(&b, &f, 4);
+  if ((b & 0x7f800000u) == 0x7f800000u) return f;
+  b = (b + 0x1000u) & ~0x1fffu;
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+}
+
+int Upload(DevBuf *buf, const void *src, size_t bytes) {
+  CE_CHECK(buf->Reserve(bytes));
+  CE_CUDA(cudaMemcpy(buf->ptr, src, bytes, cudaMemcpyHostToDevice));
+  return CE_GPU_OK;
+}
+
+int UploadPadded(DevBuf *buf, const std::vector<float> &v, int n_pad, float fill) {
+  std::vector<float> h((size_t)n_pad, fill);
+  std::copy(v.begin(), v.end(), h.begin());
+  return Upload(buf, h.data(), sizeof(float) * h.size());
+}
+
+}  // namespace
+
+int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
+               const std::vector<float> *cmvn_stats, int left, int right, int precision,
+               int device, ce_gpu_model *m) {
+  m->device = device;
+  m->precision = precision;
+  m->left = left;
+  m->right = right;
+  switch (precision) {
+    case CE_GPU_PRECISION_INT8: m->kind = kKindI8; m->n_pass = 1; break;
+    case CE_GPU_PRECISION_BF16: m->kind = kKindBF16; m->n_pass = 1; break;
+    case CE_GPU_PRECISION_FP32: m->kind = kKindTF32; m->n_pass = 3; break;
+    case CE_GPU_PRECISION_TF32: m->kind = kKindTF32; m->n_pass = 1; break;
+    default:
+      SetError("unknown precision %d", precision);
+      return CE_GPU_EINVAL;
+  }
+  CE_CHECK(CompileProgram(nn, left, right, &m->prog));
+  if ((int)prior.size() != m->prog.num_pdfs) {
+    SetError("prior has %zu entries, the nnet has %d outputs", prior.size(), m->prog.num_pdfs);
+    return CE_GPU_EINVAL;
+  }
+  if (cmvn_stats) {
+    if ((int)cmvn_stats->size() != m->prog.feat_dim + 1) {
+      SetError("cmvn stats have %zu entries, expected feat_dim + 1 = %d", cmvn_stats->size(),
+               m->prog.feat_dim + 1);
+      return CE_GPU_EINVAL;
+    }
+    m->has_cmvn = true;
+    m->cmvn_host = *cmvn_stats;
+    CE_CHECK(Upload(&m->cmvn_dev, cmvn_stats->data(), sizeof(float) * cmvn_stats->size()));
+  }
+  {  // log_prior_.ApplyLog(), src/am.cc:43-44 (logf of every entry, src/vector.cc:167-174)
+    std::vector<float> lp(prior.size());
+    for (size_t i = 0; i < prior.size(); ++i) lp[i] = logf(prior[i]);
+    CE_CHECK(Upload(&m->log_prior, lp.data(), sizeof(float) * lp.size()));
+  }
+
+  const int tile_k = KindTileK(m->kind);
+  m->blocks.resize(m->prog.blocks.size());
+  for (size_t bi = 0; bi < m->prog.blocks.size(); ++bi) {
+    const Block &B = m->prog.blocks[bi];
+    DeviceBlock &D = m->blocks[bi];
+    const HostLayer &L = nn.layers[B.linear];
+    D.meta = B;
+    D.c_pad = RoundUp(B.in_dim, tile_k);
+    const int n_taps = (int)B.taps.size();
+    D.k_total = (int64_t)n_taps * D.c_pad;
+    const int N = B.out_dim, C = B.in_dim, K = n_taps * C;
+    // per-column arrays cover every column the epilogue may touch (the next block's K padding)
+    int next_pad = N;
+    if (bi + 1 < m->prog.blocks.size()) next_pad = RoundUp(m->prog.blocks[bi + 1].in_dim, tile_k);
+    D.n_pad = RoundUp(std::max(N, next_pad), kTileN);
+    CE_CHECK(UploadPadded(&D.bias, L.b, D.n_pad, 0.0f));
+    if (B.batchnorm >= 0) {
+      CE_CHECK(UploadPadded(&D.bn_scale, nn.layers[B.batchnorm].scale, D.n_pad, 0.0f));
+      CE_CHECK(UploadPadded(&D.bn_offset, nn.layers[B.batchnorm].offset, D.n_pad, 0.0f));
+    }
+    const size_t elems = (size_t)N * (size_t)D.k_total;
+    if (m->kind == kKindI8) {
+      std::vector<uint8_t> w8((size_t)K * N);
+      QuantizeHost(L.W.data(), (int64_t)K * N, w8.data(), &D.scale_b, &D.zp_b);
+      std::vector<uint8_t> packed(elems, 0);
+      std::vector<int32_t> colsum((size_t)D.n_pad, 0);
+      for (int t = 0; t < n_taps; ++t)
+        for (int c = 0; c < C; ++c) {
+          const uint8_t *src = w8.data() + (size_t)(t * C + c) * N;
+          const size_t kk = (size_t)t * D.c_pad + c;
+          for (int n = 0; n < N; ++n) {
+            packed[(size_t)n * D.k_total + kk] = src[n];
+            colsum[n] += src[n];
+          }
+        }
+      CE_CHECK(Upload(&D.w[0], packed.data(), packed.size()));
+      CE_CHECK(Upload(&D.colsum, colsum.data(), sizeof(int32_t) * colsum.size()));
+    } else if (m->kind == kKindBF16) {
+      std::vector<uint16_t> packed(elems, 0);
+      for (int t = 0; t < n_taps; ++t)
+        for (int c = 0; c < C; ++c) {
+          const float *src = L.W.data() + (size_t)(t * C + c) * N;
+          const size_t kk = (size_t)t * D.c_pad + c;
+          for (int n = 0; n < N; ++n) packed[(size_t)n * D.k_total + kk] = Bf16Bits(src[n]);
+        }
+      CE_CHECK(Upload(&D.w[0], packed.data(), packed.size() * 2));
+    } else {
+      std::vector<float> hi(elems, 0.0f), lo;
+      if (m->n_pass == 3) lo.assign(elems, 0.0f);
+      for (int t = 0; t < n_taps; ++t)
+        for (int c = 0; c < C; ++c) {
+          const float *src = L.W.data() + (size_t)(t * C + c) * N;
+          const size_t kk = (size_t)t * D.c_pad + c;
+          for (int n = 0; n < N; ++n) {
+            const float h = Tf32Round(src[n]);
+            hi[(size_t)n * D.k_total + kk] = h;
+            if (m->n_pass == 3) lo[(size_t)n * D.k_total + kk] = src[n] - h;
+          }
+        }
+      CE_CHECK(Upload(&D.w[0], hi.data(), hi.size() * 4));
+      if (m->n_pass == 3) CE_CHECK(Upload(&D.w[1], lo.data(), lo.size() * 4));
+    }
+  }
+  if (const char *e = getenv("CE_GPU_CHUNK_ROWS")) {
+    long v = atol(e);
+    if (v >= kTileM) m->max_chunk_rows = v;
+  }
+  return CE_GPU_OK;
+}
+
+namespace {
+
+RowUse MakeRowUse(const ce_gpu_model *m, int producer /* -1 = network input */) {
+  RowUse u;
+  memset(&u, 0, sizeof(u));
+  if (producer >= 0) {
+    u.lo = m->blocks[producer].meta.cum_left;
+    u.hi = m->blocks[producer].meta.cum_right;
+  }
+  const Block &nx = m->blocks[producer + 1].meta;
+  u.next_n_taps = (int)nx.taps.size();
+  for (int t = 0; t < u.next_n_taps; ++t) u.next_tap_off[t] = nx.taps[t];
+  u.next_lo = nx.cum_left;
+  u.next_hi = nx.cum_right;
+  return u;
+}
+
+// Output rows are addressed by absolute frame index (frame_off), so loglik_dev / argmax_dev are
+// the bases of the whole batch's outputs.
+int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
+                 bool apply_cmvn, float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
+  const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
+  const int nb = (int)m->blocks.size();
+
+  // ---- row space ----
+  std::vector<int64_t> row_off64(n_utts);
+  int64_t M64 = 0;
+  for (int u = 0; u < n_utts; ++u) {
+    const int64_t T = frame_off[u + 1] - frame_off[u];
+    row_off64[u] = M64;
+    if (T > 0) M64 += (T + L + R + kTileM - 1) / kTileM * kTileM;
+  }
+  if (M64 == 0) return CE_GPU_OK;
+  if (M64 > 0x7fffff00LL) {
+    SetError("a chunk of %lld rows exceeds the 2^31 row limit", (long long)M64);
+    return CE_GPU_EINVAL;
+  }
+  const int M = (int)M64;
+  const int m_tiles = M / kTileM;
+  CE_CHECK(m->utt_table.Acquire(sizeof(UttRows) * n_utts));
+  CE_CHECK(m->tile_table.Acquire(sizeof(int32_t) * m_tiles));
+  CE_CHECK(m->outrow_table.Acquire(sizeof(int64_t) * n_utts));
+  UttRows *hu = m->utt_table.host<UttRows>();
+  int32_t *ht = m->tile_table.host<int32_t>();
+  int64_t *ho = m->outrow_table.host<int64_t>();
+  for (int u = 0; u < n_utts; ++u) {
+    const int64_t T = frame_off[u + 1] - frame_off[u];
+    hu[u].row_off = (int32_t)row_off64[u];
+    hu[u].rows = T > 0 ? (int32_t)(T + L + R) : 0;
+    ho[u] = frame_off[u];
+    const int64_t end = (u + 1 < n_utts) ? row_off64[u + 1] : M64;
+    for (int64_t t = row_off64[u] / kTileM; t < end / kTileM; ++t) ht[t] = u;
+  }
+  CE_CHECK(m->utt_table.Upload(sizeof(UttRows) * n_utts, s));
+  CE_CHECK(m->tile_table.Upload(sizeof(int32_t) * m_tiles, s));
+  CE_CHECK(m->outrow_table.Upload(sizeof(int64_t) * n_utts, s));
+  const UttRows *d_utts = m->utt_table.dev<UttRows>();
+  const int32_t *d_tile = m->tile_table.dev<int32_t>();
+
+  // ---- workspace ----
+  int wmax = 4;
+  for (const DeviceBlock &D : m->blocks) wmax = std::max(wmax, std::max(D.c_pad, RoundUp(D.meta.out_dim, 4)));
+  const int ldp = RoundUp(NP, 4);
+  CE_CHECK(m->x0.Reserve(sizeof(float) * (size_t)M * F));
+  CE_CHECK(m->logits.Reserve(sizeof(float) * (size_t)M * ldp));
+  if (m->kind == kKindI8) {
+    CE_CHECK(m->act_f32[0].Reserve(sizeof(float) * (size_t)M * wmax));
+    CE_CHECK(m->act_u8.Reserve((size_t)M * wmax));
+    CE_CHECK(m->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
+    CE_CHECK(m->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
+    CE_CHECK(m->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
+  } else if (m->kind == kKindBF16) {
+    for (int i = 0; i < 2; ++i) CE_CHECK(m->act_bf16[i].Reserve(2 * (size_t)M * wmax));
+  } else {
+    for (int i = 0; i < 2; ++i) {
+      CE_CHECK(m->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
+      if (m->n_pass == 3) CE_CHECK(m->act_lo[i].Reserve(sizeof(float) * (size_t)M * wmax));
+    }
+  }
+
+  // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155 ----
+  CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
+                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, frame_off, row_off64.data(),
+                      n_utts, F, L, R, m->x0.as<float>(), F, &m->cmvn_utts, s));
+
+  // ---- network input in the operand format of the data path ----
+  uint32_t *mm = m->minmax.as<uint32_t>();
+  QParam *qp = m->qparams.as<QParam>();
+  const int c0 = m->blocks[0].c_pad;
+  if (m->kind == kKindI8) {
+    CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
+    CE_CHECK(MinMaxLaunch(m->x0.as<float>(), F, F, M, d_tile, d_utts, MakeRowUse(m, -1), mm, s));
+    CE_CHECK(QParamsLaunch(mm, qp, n_utts, s));
+    CE_CHECK(QuantizeLaunch(m->x0.as<float>(), F, F, M, c0, d_tile, qp, m->act_u8.as<uint8_t>(),
+                            m->rowsum.as<int32_t>(), s));
+  } else if (m->kind == kKindBF16) {
+    CE_CHECK(ConvertLaunch(m->x0.as<float>(), F, F, M, c0, m->act_bf16[0].as<__nv_bfloat16>(),
+                           nullptr, nullptr, s));
+  } else {
+    CE_CHECK(ConvertLaunch(m->x0.as<float>(), F, F, M, c0, nullptr, m->act_f32[0].as<float>(),
+                           m->n_pass == 3 ? m->act_lo[0].as<float>() : nullptr, s));
+  }
+
+  m->kept_valid = false;
+  for (int b = 0; b < nb; ++b) {
+    const DeviceBlock &D = m->blocks[b];
+    const bool last = (b == nb - 1);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    GemmOperands ops;
+    memset(&ops, 0, sizeof(ops));
+    a.M = M;
+    a.N = D.meta.out_dim;
+    a.c_pad = D.c_pad;
+    a.n_taps = (int)D.meta.taps.size();
+    for (int t = 0; t < a.n_taps; ++t) a.tap_off[t] = D.meta.taps[t];
+    a.n_pass = m->n_pass;
+    if (m->n_pass == 3) {                                // small terms first: lo*hi, hi*lo, hi*hi
+      a.pass_a[0] = 1; a.pass_b[0] = 0;
+      a.pass_a[1] = 0; a.pass_b[1] = 1;
+      a.pass_a[2] = 0; a.pass_b[2] = 0;
+    }
+    a.bias = D.bias.as<float>();
+    a.relu = D.meta.relu ? 1 : 0;
+    if (D.meta.batchnorm >= 0) {
+      a.bn_scale = D.bn_scale.as<float>();
+      a.bn_offset = D.bn_offset.as<float>();
+    }
+    a.tile_utt = d_tile;
+    a.utts = d_utts;
+    ops.rows_a = M;
+    ops.rows_b = D.meta.out_dim;
+    ops.k_total = D.k_total;
+    ops.b[0] = D.w[0].ptr;
+    ops.b[1] = D.w[1].ptr;
+    const int next_c = last ? 0 : m->blocks[b + 1].c_pad;
+
+    if (m->kind == kKindI8) {
+      ops.a[0] = m->act_u8.ptr;
+      a.a_rowsum = m->rowsum.as<int32_t>();
+      a.b_colsum = D.colsum.as<int32_t>();
+      a.zp_b = D.zp_b;
+      a.scale_b = D.scale_b;
+      a.k_true = a.n_taps * D.meta.in_dim;
+      a.qa = qp + (size_t)b * n_utts;
+      a.out_f32 = last ? m->logits.as<float>() : m->act_f32[0].as<float>();
+      a.ld_out = last ? ldp : RoundUp(a.N, 4);
+      a.n_store = a.N;
+      if (!last) {
+        a.minmax = mm + 2 * (size_t)(b + 1) * n_utts;
+        const RowUse ru = MakeRowUse(m, b);
+        a.mm_lo = ru.lo; a.mm_hi = ru.hi;
+        a.next_n_taps = ru.next_n_taps;
+        memcpy(a.next_tap_off, ru.next_tap_off, sizeof(a.next_tap_off));
+        a.next_lo = ru.next_lo; a.next_hi = ru.next_hi;
+      }
+      if (m->keep_acc == b) {
+        CE_CHECK(m->acc_dump.Reserve(sizeof(int32_t) * (size_t)M * a.ld_out));
+        a.out_acc = m->acc_dump.as<int32_t>();
+        m->kept_row_off.resize(n_utts);
+        m->kept_rows.resize(n_utts);
+        for (int u = 0; u < n_utts; ++u) {
+          m->kept_row_off[u] = hu[u].row_off;
+          m->kept_rows[u] = hu[u].rows;
+        }
+        m->kept_lo = D.meta.cum_left;
+        m->kept_hi = D.meta.cum_right;
+        m->kept_cols = a.N;
+        m->kept_ld = a.ld_out;
+        m->kept_valid = true;
+      }
+    } else if (m->kind == kKindBF16) {
+      ops.a[0] = m->act_bf16[b & 1].ptr;
+      if (last) {
+        a.out_f32 = m->logits.as<float>();
+        a.ld_out = ldp;
+        a.n_store = a.N;
+      } else {
+        a.out_bf16 = m->act_bf16[(b + 1) & 1].as<__nv_bfloat16>();
+        a.ld_out = next_c;
+        a.n_store = next_c;
+      }
+    } else {
+      ops.a[0] = m->act_f32[b & 1].ptr;
+      ops.a[1] = m->n_pass == 3 ? m->act_lo[b & 1].ptr : nullptr;
+      if (last) {
+        a.out_f32 = m->logits.as<float>();
+        a.ld_out = ldp;
+        a.n_store = a.N;
+      } else {
+        a.out_f32 = m->act_f32[(b + 1) & 1].as<float>();
+        a.out_lo = m->n_pass == 3 ? m->act_lo[(b + 1) & 1].as<float>() : nullptr;
+        a.round_tf32 = 1;
+        a.ld_out = next_c;
+        a.n_store = next_c;
+      }
+    }
+    CE_CHECK(GemmLaunch(m->kind, ops, a, s));
+
+    if (m->kind == kKindI8 && !last) {
+      QParam *q_next = qp + (size_t)(b + 1) * n_utts;
+      CE_CHECK(QParamsLaunch(mm + 2 * (size_t)(b + 1) * n_utts, q_next, n_utts, s));
+      CE_CHECK(QuantizeLaunch(m->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile, q_next,
+                              m->act_u8.as<uint8_t>(), m->rowsum.as<int32_t>(), s));
+    }
+  }
+
+  CE_CHECK(FinalizeLaunch(m->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
+                          m->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
+                          m->log_prior.as<float>(), loglik_dev, NP, argmax_dev, s));
+  return CE_GPU_OK;
+}
+
+}  // namespace
+
+int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
+                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
+  if (apply_cmvn && !m->has_cmvn) {
+    SetError("the model was loaded without CMVN statistics");
+    return CE_GPU_EINVAL;
+  }
+  const int L = m->left, R = m->right, NP = m->prog.num_pdfs;
+  const bool ll_host = loglik && !IsDevicePtr(loglik);
+  const bool am_host = argmax && !IsDevicePtr(argmax);
+  int u0 = 0;
+  while (u0 < n_utts) {
+    int u1 = u0;
+    int64_t rows = 0;
+    while (u1 < n_utts) {
+      const int64_t T = frame_off[u1 + 1] - frame_off[u1];
+      const int64_t r = T > 0 ? (T + L + R + kTileM - 1) / kTileM * kTileM : 0;
+      if (u1 > u0 && rows + r > m->max_chunk_rows) break;
+      rows += r;
+      ++u1;
+    }
+    const int64_t f0 = frame_off[u0], nf = frame_off[u1] - f0;
+    float *ll_dev = loglik;
+    int32_t *am_dev = argmax;
+    if (ll_host) {
+      CE_CHECK(m->stage_loglik.Reserve(sizeof(float) * (size_t)nf * NP));
+      ll_dev = m->stage_loglik.as<float>() - f0 * NP;     // row f0 lands on the staging buffer's row 0
+    }
+    if (am_host) {
+      CE_CHECK(m->stage_argmax.Reserve(sizeof(int32_t) * (size_t)nf));
+      am_dev = m->stage_argmax.as<int32_t>() - f0;
+    }
+    CE_CHECK(ForwardChunk(m, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, s));
+    if (ll_host && nf > 0) {
+      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, m->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
+                              cudaMemcpyDeviceToHost, s));
+    }
+    if (am_host && nf > 0) {
+      CE_CUDA(cudaMemcpyAsync(argmax + f0, m->stage_argmax.ptr, sizeof(int32_t) * (size_t)nf,
+                              cudaMemcpyDeviceToHost, s));
+    }
+    if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));
+    u0 = u1;
+  }
+  return CE_GPU_OK;
+}
+
+}  // namespace ce

@@ -1,0 +1,77 @@
+// nnet.h -- the acoustic model on the device: packed weights, workspace, forward pass.
+#ifndef CE_GPU_NNET_H_
+#define CE_GPU_NNET_H_
+
+#include <vector>
+
+#include "common.h"
+#include "gemm.h"
+#include "model.h"
+#include "nnet_kernels.h"
+
+namespace ce {
+
+struct DeviceBlock {
+  Block meta;
+  int c_pad = 0;             // input channels per tap, padded to the K tile of the data path
+  int n_pad = 0;             // length of the per-column parameter arrays (multiple of kTileN)
+  int64_t k_total = 0;       // taps * c_pad
+  DevBuf w[2];               // packed weights [out_dim x k_total]: (hi, lo) / only
+  DevBuf bias, bn_scale, bn_offset, colsum;
+  float scale_b = 0.0f;      // Quantize(W_) of the whole [in x out] matrix
+  int32_t zp_b = 0;
+};
+
+}  // namespace ce
+
+// The opaque handle of include/ce_gpu.h.
+struct ce_gpu_model {
+  int device = 0;
+  int precision = 0;
+  int kind = 0;              // GemmKind
+  int n_pass = 1;
+  int left = 0, right = 0;
+  ce::Program prog;
+  std::vector<ce::DeviceBlock> blocks;
+  ce::DevBuf log_prior;      // log(prior), src/am.cc:43-44
+  bool has_cmvn = false;
+  std::vector<float> cmvn_host;   // num_mel sums + count
+  ce::DevBuf cmvn_dev;
+  int64_t max_chunk_rows = 65536;
+
+  // ---- workspace (one forward call at a time per handle) ----
+  ce::DevBuf stage_pcm, stage_feats, stage_loglik, stage_argmax;
+  ce::DevBuf feats;                    // fbank output / staged features [frames x feat_dim]
+  ce::DevBuf x0;                       // padded fp32 input [M x feat_dim]
+  ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits, acc_dump;
+  ce::DevBuf minmax, qparams;
+  ce::Table fbank_chunks, cmvn_utts, utt_table, tile_table, outrow_table;
+  cudaStream_t own_stream = nullptr;
+
+  // ---- debug: kept accumulators ----
+  int keep_acc = -1;
+  std::vector<int32_t> kept_row_off, kept_rows;   // per utterance of the last call
+  int kept_lo = 0, kept_hi = 0, kept_cols = 0;
+  int64_t kept_ld = 0;
+  bool kept_valid = false;
+
+  ~ce_gpu_model();
+};
+
+namespace ce {
+
+// Loads and packs the model onto the current device.
+int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
+               const std::vector<float> *cmvn_stats, int left, int right, int precision,
+               int device, ce_gpu_model *m);
+
+// feats_dev: [total_frames x feat_dim] fp32 on the device, utterance u = rows
+// [frame_off[u], frame_off[u+1]).  apply_cmvn: run the online CMVN with the model's global
+// stats while building the padded network input.  loglik [total_frames x num_pdfs] and
+// argmax [total_frames] may each be nullptr, a device pointer, or a host pointer (host outputs
+// are copied back chunk by chunk and are complete on return).
+int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
+                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s);
+
+}  // namespace ce
+#endif  // CE_GPU_NNET_H_

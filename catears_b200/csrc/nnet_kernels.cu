@@ -1,0 +1,263 @@
+// nnet_kernels.cu -- the memory-bound kernels around the tensor-core GEMMs (K5, K6).
+//
+//   minmax_kernel     FindMinMax                    src/matrix.cc:329-345   (layer-0 input)
+//   qparams_kernel    ComputeQuantizationParams     src/matrix.cc:348-362
+//   quantize_kernel   Quantize                      src/matrix.cc:366-387   (+ row sums of the codes
+//                     for the zero-point correction of internal/unpack.h:118-125)
+//   convert_kernel    fp32 -> bf16 / (tf32 hi, lo) operand formats of the float paths
+//   finalize_kernel   LogSoftmaxLayer src/nnet.cc:137-146 (ApplyLogSoftMax src/vector.cc:110-122)
+//                     + "row -= log_prior" src/am.cc:109-112 + argmax, written as compact rows
+#include "nnet_kernels.h"
+
+#include <float.h>
+
+namespace ce {
+namespace {
+
+__device__ __forceinline__ bool RowUsed(int pos, int P, const RowUse &u) {
+  if (pos < u.lo || pos >= P - u.hi) return false;
+  if (u.next_n_taps == 0) return true;
+  for (int t = 0; t < u.next_n_taps; ++t) {
+    const int o = pos - u.next_tap_off[t];
+    if (o >= u.next_lo && o < P - u.next_hi) return true;
+  }
+  return false;
+}
+
+__global__ void init_minmax_kernel(uint32_t *mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    mm[2 * i] = OrderedFromFloat(FLT_MAX);               // matrix.cc:330
+    mm[2 * i + 1] = OrderedFromFloat(FLT_MIN);           // matrix.cc:331 (smallest positive normal)
+  }
+}
+
+// One warp per row of x [M x ld] (first C columns).
+__global__ void __launch_bounds__(256)
+minmax_kernel(const float *__restrict__ x, int64_t ld, int C, int M,
+              const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts, RowUse use,
+              uint32_t *__restrict__ minmax) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+  int pos = row, P = M;
+  if (utts) {
+    pos = row - utts[utt].row_off;
+    P = utts[utt].rows;
+  }
+  if (!RowUsed(pos, P, use)) return;
+  float vmin = FLT_MAX, vmax = -FLT_MAX;
+  const float *r = x + (int64_t)row * ld;
+  for (int c = lane; c < C; c += 32) {
+    const float v = r[c];
+    vmin = (v < vmin) ? v : vmin;
+    vmax = (v > vmax) ? v : vmax;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane == 0 && vmin <= vmax) {
+    atomicMin(minmax + 2 * utt, OrderedFromFloat(vmin));
+    atomicMax(minmax + 2 * utt + 1, OrderedFromFloat(vmax));
+  }
+}
+
+__global__ void qparams_kernel(const uint32_t *__restrict__ minmax, QParam *__restrict__ q, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mn = FloatFromOrdered(minmax[2 * i]);
+  const float mx = FloatFromOrdered(minmax[2 * i + 1]);
+  const double scale = (double)__fsub_rn(mx, mn) / 255.0;             // matrix.cc:354
+  const double fzp = (double)(-mn) / scale;                           // matrix.cc:357
+  q[i].zero_point = (int32_t)round(fzp);                              // matrix.cc:358
+  q[i].scale = (float)scale;                                          // matrix.cc:361
+}
+
+__device__ __forceinline__ uint32_t QuantOne(float v, float scale, float zp) {
+  float q = __fadd_rn(__fdiv_rn(v, scale), zp);                       // matrix.cc:383
+  q = (q < 255.0f) ? q : ((255.0f < q) ? 255.0f : q);                 // std::min(val, 255.0f)
+  q = (0.0f < q) ? q : 0.0f;                                          // std::max(0.0f, .) (NaN -> 0)
+  return (uint32_t)roundf(q);                                         // matrix.cc:385
+}
+
+// One warp per row: x [M x ld_in] fp32 (C columns) -> q [M x c_pad] u8 (zero padded) and
+// rowsum[row] = sum of the C codes.
+__global__ void __launch_bounds__(256)
+quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_pad,
+                const int32_t *__restrict__ tile_utt, const QParam *__restrict__ qp,
+                uint8_t *__restrict__ q, int32_t *__restrict__ rowsum) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+  const QParam p = qp[utt];
+  const float zp = (float)p.zero_point;
+  const float *r = x + (int64_t)row * ld_in;
+  uint32_t *o = reinterpret_cast<uint32_t *>(q + (int64_t)row * c_pad);
+  int32_t sum = 0;
+  const bool vec = ((ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int c4 = lane * 4; c4 < c_pad; c4 += 128) {
+    uint32_t code[4] = {0, 0, 0, 0};
+    if (vec && c4 + 4 <= C) {
+      const float4 f = *reinterpret_cast<const float4 *>(r + c4);
+      code[0] = QuantOne(f.x, p.scale, zp);
+      code[1] = QuantOne(f.y, p.scale, zp);
+      code[2] = QuantOne(f.z, p.scale, zp);
+      code[3] = QuantOne(f.w, p.scale, zp);
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (c4 + j < C) code[j] = QuantOne(r[c4 + j], p.scale, zp);
+    }
+    sum += (int32_t)(code[0] + code[1] + code[2] + code[3]);
+    o[c4 >> 2] = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  if (lane == 0 && rowsum) rowsum[row] = sum;
+}
+
+__device__ __forceinline__ float RoundTf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// x [M x ld_in] fp32 (C columns) -> zero-padded [M x c_pad] bf16, or fp32 hi (+ lo).
+__global__ void __launch_bounds__(256)
+convert_kernel(const float *__restrict__ x, int64_t ld_in, int C, int64_t M, int c_pad,
+               __nv_bfloat16 *__restrict__ out_bf16, float *__restrict__ out_hi,
+               float *__restrict__ out_lo) {
+  const int64_t n = M * c_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / c_pad;
+    const int c = (int)(i % c_pad);
+    const float v = (c < C) ? x[row * ld_in + c] : 0.0f;
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+    if (out_hi) {
+      const float h = RoundTf32(v);
+      out_hi[i] = h;
+      if (out_lo) out_lo[i] = v - h;
+    }
+  }
+}
+
+// One warp per padded row; valid rows only.  Numerically stable log-sum-exp (the reference
+// has no max subtraction, src/vector.cc:110-122; results agree to fp32 rounding while the
+// reference's sum is finite).
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
+                const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
+                const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
+                const float *__restrict__ log_prior, float *__restrict__ loglik, int64_t ld_out,
+                int32_t *__restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int utt = tile_utt[row / kTileM];
+  const UttRows ur = utts[utt];
+  const int pos = row - ur.row_off;
+  if (pos < left || pos >= ur.rows - right) return;
+  const int64_t orow = out_row_off[utt] + (pos - left);
+  const float *x = logits + (int64_t)row * ld;
+
+  float lse = 0.0f;
+  if (log_softmax) {
+    float m = -FLT_MAX;
+    for (int c = lane; c < N; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.0f;
+    for (int c = lane; c < N; c += 32) s += expf(x[c] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    lse = m + logf(s);
+  }
+  float best = -FLT_MAX;
+  int best_i = 0x7fffffff;
+  float *y = loglik ? loglik + orow * ld_out : nullptr;
+  for (int c = lane; c < N; c += 32) {
+    float v = x[c];
+    if (log_softmax) v = __fsub_rn(v, lse);              // x -= log(sum)      vector.cc:120
+    v = __fsub_rn(v, log_prior[c]);                      // AddVec(-1, log_prior_)  am.cc:111
+    if (y) y[c] = v;
+    if (v > best) {                                      // first maximum wins
+      best = v;
+      best_i = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if (argmax && lane == 0) argmax[orow] = best_i == 0x7fffffff ? 0 : best_i;
+}
+
+// Copies the valid rows [lo, P - hi) of one utterance out of a padded int32 matrix.
+}  // namespace
+
+int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s) {
+  if (n <= 0) return CE_GPU_OK;
+  init_minmax_kernel<<<(n + 255) / 256, 256, 0, s>>>(mm, n);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_utt,
+                 const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s) {
+  if (M <= 0) return CE_GPU_OK;
+  minmax_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld, C, M, tile_utt, utts, use, minmax);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s) {
+  if (n <= 0) return CE_GPU_OK;
+  qparams_kernel<<<(n + 127) / 128, 128, 0, s>>>(minmax, q, n);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const int32_t *tile_utt,
+                   const QParam *qp, uint8_t *q, int32_t *rowsum, cudaStream_t s) {
+  if (M <= 0) return CE_GPU_OK;
+  if (c_pad % 4 != 0) {
+    SetError("QuantizeLaunch: c_pad %d is not a multiple of 4", c_pad);
+    return CE_GPU_EINVAL;
+  }
+  quantize_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
+                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s) {
+  if (M <= 0) return CE_GPU_OK;
+  const int64_t n = M * c_pad;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  convert_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, out_bf16, out_hi, out_lo);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
+                   const UttRows *utts, const int64_t *out_row_off, int left, int right,
+                   bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
+                   int32_t *argmax, cudaStream_t s) {
+  if (M <= 0) return CE_GPU_OK;
+  finalize_kernel<<<(M + 7) / 8, 256, 0, s>>>(logits, ld, N, M, tile_utt, utts, out_row_off, left,
+                                             right, log_softmax ? 1 : 0, log_prior, loglik, ld_out,
+                                             argmax);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+}  // namespace ce

@@ -1,0 +1,32 @@
+// nnet_kernels.h -- launchers of the memory-bound kernels around the GEMMs (nnet_kernels.cu).
+#ifndef CE_GPU_NNET_KERNELS_H_
+#define CE_GPU_NNET_KERNELS_H_
+
+#include "gemm.h"
+
+namespace ce {
+
+// Which rows of an utterance block take part in FindMinMax: rows in [lo, P - hi) that the
+// consuming layer's Splice+Narrow reads (matters for very short utterances).
+struct RowUse {
+  int32_t lo, hi;
+  int32_t next_n_taps;               // 0 = every row in range
+  int32_t next_tap_off[kMaxTaps];
+  int32_t next_lo, next_hi;
+};
+
+int InitMinMaxLaunch(uint32_t *mm, int n_pairs, cudaStream_t s);
+int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_utt,
+                 const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s);
+int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s);
+int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const int32_t *tile_utt,
+                   const QParam *qp, uint8_t *q, int32_t *rowsum, cudaStream_t s);
+int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
+                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s);
+int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
+                   const UttRows *utts, const int64_t *out_row_off, int left, int right,
+                   bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
+                   int32_t *argmax, cudaStream_t s);
+
+}  // namespace ce
+#endif  // CE_GPU_NNET_KERNELS_H_

@@ -1,0 +1,159 @@
+/* ce_gpu.h -- C ABI of libce_gpu.so: the B200 (sm_100a) replacement for the
+ * CatEars acoustic front-end + acoustic-model forward pass.
+ *
+ * What this boundary replaces in the reference (ishine/CatEars):
+ *
+ *   ce_gpu_fbank      WaveReader::Process   src/pcm_reader.cc:148-190  (int16 -> float, unscaled)
+ *                     Fbank::Process        src/fbank.cc:265-314       (all frames of an utterance)
+ *   ce_gpu_cmvn       CMVN::GetFrame        src/cmvn.cc:100-110        (frames 0..T-1 in order)
+ *   ce_gpu_nnet       AcousticModel::Process / EndOfStream  src/am.cc:115-164, i.e.
+ *                     ComputeBatch src/am.cc:82-113 = replicate padding + Nnet::Propagate
+ *                     (src/nnet.cc:295-307) + "row -= log_prior"
+ *   ce_gpu_forward    the body of ce_stt_process/ce_stt_end_of_stream between WaveReader and
+ *                     Decoder::Process      src/ce_stt.cc:307-331,349-357
+ *   ce_gpu_model_load AcousticModel::Read   src/am.cc:26-64 (+ Nnet::Read src/nnet.cc:273-293)
+ *   ce_gpu_quantize   Quantize              src/matrix.cc:366-387
+ *   ce_gpu_gemm_u8    MatMat_U8U8F32        src/matrix.cc:389-420
+ *   ce_gpu_last_error ce_stt_last_error     src/ce_stt.cc:375-377 (thread-local here)
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every DATA pointer (pcm, feats, loglik, argmax, A, B, C...)
+ *     may be a device pointer on the handle's device or a host pointer (pinned or pageable);
+ *     host buffers are staged through the handle's own pinned/device workspace inside the call.
+ *     OFFSET arrays (utt_sample_offsets, utt_frame_offsets) are always HOST memory.
+ *   - Batches are ragged: utterance u owns samples [off[u], off[u+1]) of `pcm` and rows
+ *     [foff[u], foff[u+1]) of every per-frame output.  T_u = off<400 ? 0 : 1+(n_u-400)/160
+ *     (snip-edges, src/fbank.cc:35-42).  Utterances with T_u == 0 produce no rows.
+ *   - `stream` is a cudaStream_t (NULL = the legacy default stream).  Calls return after the
+ *     work is enqueued, except that host OUTPUT buffers are complete on return.
+ *   - Return value: 0 on success, a negative CE_GPU_E* code otherwise; the message is in
+ *     ce_gpu_last_error().  There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with CE_GPU_ENODEVICE.
+ *   - One handle per device; calls on one handle must not overlap in time (they share its
+ *     workspace); distinct handles are independent.
+ */
+#ifndef CE_GPU_H_
+#define CE_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CE_GPU_OK 0
+#define CE_GPU_EINVAL (-1)     /* bad argument                                  */
+#define CE_GPU_EIO (-2)        /* file missing / corrupt (Status::IOError/Corruption) */
+#define CE_GPU_ECUDA (-3)      /* CUDA runtime / driver error                   */
+#define CE_GPU_ENODEVICE (-4)  /* no usable sm_100 device                       */
+#define CE_GPU_ENOMEM (-5)
+#define CE_GPU_EUNSUPPORTED (-6) /* layer stack the GPU program cannot express  */
+
+/* Arithmetic of the Linear layers. */
+#define CE_GPU_PRECISION_INT8 0  /* u8 x u8 -> s32, gemmlowp-compatible (bit-exact accumulators) */
+#define CE_GPU_PRECISION_BF16 1  /* bf16 x bf16 -> fp32                         */
+#define CE_GPU_PRECISION_FP32 2  /* 3xTF32 error-compensated, fp32-class accuracy */
+#define CE_GPU_PRECISION_TF32 3  /* single-pass TF32                            */
+
+typedef struct ce_gpu_model ce_gpu_model_t;
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *ce_gpu_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). Never fails. */
+int ce_gpu_device_count(void);
+
+/* Library/ABI version (for the loader check in tests): 10000*major + 100*minor + patch. */
+int ce_gpu_version(void);
+
+/* ---- model ---------------------------------------------------------------- */
+
+/* Loads an NN02 nnet + VEC0 prior (+ optional VEC0 CMVN global stats, NULL = no CMVN, which is
+ * what src/ce_stt.cc actually does) onto `device`, packing/quantising the weights once.
+ * left/right context are the AM's (config-file) values, src/am.cc:48-50. */
+ce_gpu_model_t *ce_gpu_model_load(const char *nnet_path, const char *prior_path,
+                                  const char *cmvn_stats_path, int left_context,
+                                  int right_context, int precision, int device);
+
+/* Same, from the reference's "key = value" config file (keys nnet, prior, left_context,
+ * right_context, num_pdfs [, cmvn_stats]), src/am.cc:26-64, src/configuration.cc:14-88. */
+ce_gpu_model_t *ce_gpu_model_load_config(const char *config_path, int precision, int device);
+
+void ce_gpu_model_free(ce_gpu_model_t *m);
+
+/* Any out pointer may be NULL. */
+int ce_gpu_model_info(const ce_gpu_model_t *m, int *num_pdfs, int *left_context,
+                      int *right_context, int *feat_dim, int *precision, int *device);
+
+/* ---- stage-level entry points (also what the parity tests call) ----------- */
+
+/* Frame bookkeeping only (host): fills utt_frame_offsets[n_utts+1]; returns total frames
+ * (>= 0) or a negative error. */
+int64_t ce_gpu_frame_offsets(const int64_t *utt_sample_offsets, int n_utts,
+                             int64_t *utt_frame_offsets);
+
+/* Log-mel filterbank of int16 PCM: feats[total_frames x num_mel] fp32, packed by utterance.
+ * num_mel 40 is the reference's PK_FBANK_DIM; other sizes (<= 128) are an extension. */
+int ce_gpu_fbank(const int16_t *pcm, const int64_t *utt_sample_offsets, int n_utts,
+                 int num_mel, float *feats, int device, void *stream);
+
+/* Online mean-only CMVN with the reference's 600-frame window / 200-frame global smoothing.
+ * global_stats: num_mel sums then the count (HOST pointer, num_mel+1 floats).  In place
+ * (out == feats) is allowed. */
+int ce_gpu_cmvn(const float *global_stats, const float *feats,
+                const int64_t *utt_frame_offsets, int n_utts, int num_mel, float *out,
+                int device, void *stream);
+
+/* 512-point forward real FFT of n_frames rows of 512 floats, packed output
+ * [Re0, Re256, Re1, Im1, ...] as SRFFT::Compute (src/srfft.cc:370).  Test hook for the FFT
+ * inside ce_gpu_fbank (the same device code). */
+int ce_gpu_rfft512(const float *in, int n_frames, float *out, int device, void *stream);
+
+/* Acoustic model on ready features [total_frames x feat_dim]: per utterance replicate-pad,
+ * propagate, subtract log prior.  loglik[total_frames x num_pdfs] (may be NULL if only argmax
+ * is wanted); argmax[total_frames] int32 (may be NULL). */
+int ce_gpu_nnet(ce_gpu_model_t *m, const float *feats, const int64_t *utt_frame_offsets,
+                int n_utts, float *loglik, int32_t *argmax, void *stream);
+
+/* The whole path: PCM -> fbank -> [CMVN if the model has stats] -> AM.
+ * utt_frame_offsets_out (HOST, n_utts+1) may be NULL. */
+int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sample_offsets,
+                   int n_utts, float *loglik, int32_t *argmax,
+                   int64_t *utt_frame_offsets_out, void *stream);
+
+/* Debug/parity hook (int8 models): after the next ce_gpu_nnet/ce_gpu_forward call the int32
+ * accumulators of the `linear_ordinal`-th Linear layer are kept; fetch them with
+ * ce_gpu_nnet_get_acc.  Pass -1 to disable. */
+int ce_gpu_nnet_keep_acc(ce_gpu_model_t *m, int linear_ordinal);
+/* Copies rows of utterance `utt` of the kept accumulators: acc[rows x cols] (HOST). */
+int ce_gpu_nnet_get_acc(ce_gpu_model_t *m, int utt, int32_t *acc, int64_t cap, int *rows,
+                        int *cols);
+
+/* ---- matrix-level entry points --------------------------------------------- */
+
+/* Quantize (src/matrix.cc:366-387) of a contiguous [rows x cols] fp32 matrix to u8 with one
+ * (scale, zero_point) for the whole matrix; scale/zero_point are HOST out-pointers. */
+int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, float *scale,
+                    int32_t *zero_point, int device, void *stream);
+
+/* MatMat_U8U8F32 (src/matrix.cc:389-420): A[m x k] u8, B[k x n] u8, both row-major;
+ * C[m x n] = (float)acc * (scale_a*scale_b), acc = sum_k (A-zp_a)(B-zp_b) in int32.
+ * acc (nullable) receives the int32 accumulators. */
+int ce_gpu_gemm_u8(const uint8_t *a, float scale_a, int32_t zp_a, const uint8_t *b,
+                   float scale_b, int32_t zp_b, int m, int n, int k, float *c, int32_t *acc,
+                   int device, void *stream);
+
+/* C[m x n] = A[m x k] * B[k x n], fp32 in/out, `precision` one of BF16/FP32/TF32 (tensor-core
+ * replacement for MatMat / cblas_sgemm, src/matrix.cc:300-323). */
+int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *c,
+                    int precision, int device, void *stream);
+
+/* ---- instrumentation -------------------------------------------------------- */
+
+/* Number of kernels this library has launched on this thread since the last reset. */
+int64_t ce_gpu_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CE_GPU_H_ */

@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: libce_gpu.so loads, exports every symbol that
+include/ce_gpu.h declares, and every compute entry point fails loudly (no CPU fallback) when
+there is no CUDA device.  No compute calls succeed without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from catears_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ce_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ce_gpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    names = _declared()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), "libce_gpu.so does not export %s" % n
+    assert sorted(api.EXPORTS) == names
+
+
+def test_version_and_error_string():
+    L = api.lib()
+    assert L.ce_gpu_version() >= 100
+    assert isinstance(api.last_error(), str)
+
+
+def test_frame_offsets_host_logic():
+    """CalcNumFrames, src/fbank.cc:35-42: T = n < 400 ? 0 : 1 + (n - 400) / 160."""
+    sizes = [0, 1, 399, 400, 401, 559, 560, 7802, 160000]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    fo = api.frame_offsets(off)
+    want = [0 if n < 400 else 1 + (n - 400) // 160 for n in sizes]
+    assert list(np.diff(fo)) == want
+    assert want[-1] == 998 and want[-2] == 47
+    with pytest.raises(api.CeGpuError):
+        api.frame_offsets([0, 10, 5])
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device path cannot be exercised")
+    assert api.device_count() == 0
+    pcm = np.zeros(1600, np.int16)
+    with pytest.raises(api.CeGpuError, match="no CUDA device|CUDA"):
+        api.fbank(pcm)
+    with pytest.raises(api.CeGpuError):
+        api.cmvn(np.ones(41, np.float32), np.zeros((3, 40), np.float32))
+    with pytest.raises(api.CeGpuError):
+        api.gemm_u8(np.zeros((4, 4), np.uint8), 1.0, 0, np.zeros((4, 4), np.uint8), 1.0, 0)
+    with pytest.raises(api.CeGpuError):
+        api.quantize(np.zeros((4, 4), np.float32))
+
+
+def test_model_load_errors(tmp_path, small_model):
+    """Status::IOError / Corruption paths of AcousticModel::Read (src/am.cc:26-64) surface as a
+    NULL handle + message; without a device the loader stops at the device check."""
+    with pytest.raises(api.CeGpuError, match="unable to open"):
+        api.AcousticModelGpu(nnet=str(tmp_path / "missing.nnet"), prior=small_model["prior"],
+                             left_context=13, right_context=13)
+    bad = tmp_path / "bad.nnet"
+    bad.write_bytes(b"NN01" + b"\0" * 12)
+    with pytest.raises(api.CeGpuError, match="section name mismatch"):
+        api.AcousticModelGpu(nnet=str(bad), prior=small_model["prior"], left_context=13,
+                             right_context=13)
+    conf = tmp_path / "x.conf"
+    conf.write_text("nnet = a = b\n")
+    with pytest.raises(api.CeGpuError, match="Unexpected line"):
+        api.AcousticModelGpu(config=str(conf))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(api.CeGpuError, match="no CUDA device"):
+            api.AcousticModelGpu(config=small_model["conf"])

@@ -1,0 +1,153 @@
+"""GPU parity: fbank (K1), 512-point real FFT and online CMVN (K2) through the C ABI against
+the oracle, the reference's Kaldi goldens and size-independent properties."""
+import numpy as np
+import pytest
+
+from catears_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    """north_star: fbank/CMVN within 1e-4 relative; relative to max(|ref|, 1)."""
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)))
+
+
+def test_rfft512_known_dft():
+    rng = np.random.default_rng(0)
+    x = (1000 * rng.standard_normal((37, 512))).astype(np.float32)
+    out = api.rfft512(x)
+    X = np.fft.rfft(x.astype(np.float64), axis=1)
+    scale = np.abs(X).max()
+    assert np.abs(out[:, 0] - X[:, 0].real).max() < 2e-6 * scale
+    assert np.abs(out[:, 1] - X[:, 256].real).max() < 2e-6 * scale
+    got = out[:, 2::2] + 1j * out[:, 3::2]
+    assert np.abs(got - X[:, 1:256]).max() < 2e-6 * scale
+
+
+def test_rfft512_vs_oracle(port):
+    rng = np.random.default_rng(1)
+    x = (1000 * rng.standard_normal((8, 512))).astype(np.float32)
+    out = api.rfft512(x)
+    for i in range(8):
+        want = port.srfft(x[i])
+        assert np.abs(out[i] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_fbank_kaldi_golden(golden):
+    """test/fbank_test.cc:24-60: en-us-hello.wav -> 47x40 vs Kaldi compute-fbank-feats, 1e-4 abs."""
+    fb = api.fbank(golden["hello_pcm"])
+    assert fb.shape == (47, 40)
+    assert np.abs(fb - golden["kaldi_fbank"]).max() < 1e-4
+
+
+def test_fbank_vs_reference_vectors(golden):
+    for key, pcm in (("fbank40_en-us-hello", golden["hello_pcm"]),
+                     ("fbank40_en-us-cat", golden["cat_pcm"]),
+                     ("fbank40_synth0_1s", synth.synth_utterance(0, 16000))):
+        want = golden["ref"][key]
+        got = api.fbank(pcm)
+        assert got.shape == want.shape
+        assert rel_err(got, want) < 1e-4, key
+
+
+def test_fbank_ragged_batch_vs_oracle(port):
+    """Ragged batch incl. empty, < 1 frame, exactly 1 frame, chunk boundaries (32-frame CTAs)."""
+    sizes = [0, 399, 400, 559, 560, 400 + 160 * 31, 400 + 160 * 32, 400 + 160 * 33, 16000, 7802, 1, 48000]
+    rng = np.random.default_rng(5)
+    utts = [np.clip(np.rint(3000 * rng.standard_normal(n)), -32768, 32767).astype(np.int16) for n in sizes]
+    pcm = np.concatenate(utts)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    got = api.fbank(pcm, off)
+    fo = api.frame_offsets(off)
+    assert got.shape[0] == fo[-1]
+    for u, x in enumerate(utts):
+        T = port.num_frames(x.size)
+        assert fo[u + 1] - fo[u] == T
+        if T:
+            assert rel_err(got[fo[u]:fo[u + 1]], port.fbank(x)) < 1e-4, sizes[u]
+
+
+def test_fbank_extreme_inputs(port):
+    """Silence (floor -> log(FLT_EPSILON)), full-scale square wave, DC."""
+    n = 4000
+    cases = {
+        "zeros": np.zeros(n, np.int16),
+        "dc": np.full(n, 12345, np.int16),
+        "square": np.where(np.arange(n) % 50 < 25, 32767, -32768).astype(np.int16),
+        "impulse": np.eye(1, n, 777, dtype=np.int16)[0] * 32767,
+    }
+    for name, x in cases.items():
+        got, want = api.fbank(x), port.fbank(x)
+        assert got.shape == want.shape
+        if name in ("zeros", "dc"):
+            assert np.allclose(got, np.log(np.float32(1.1920929e-7)), atol=1e-5), name
+        else:
+            assert rel_err(got, want) < 1e-4, name
+
+
+def test_fbank_80_bins_vs_port(port):
+    pcm = synth.synth_utterance(3, 16000)
+    got = api.fbank(pcm, num_mel=80)
+    want = port.fbank(pcm, mel=80)
+    assert got.shape == want.shape == (98, 80)
+    assert rel_err(got, want) < 1e-4
+
+
+def test_fbank_device_buffers_and_batch_equals_singles():
+    import torch
+    pcm, off = synth.synth_batch(5, 16000)
+    batch = api.fbank(pcm, off)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_out = torch.zeros((batch.shape[0], 40), dtype=torch.float32, device="cuda")
+    api.fbank(d_pcm, off, out=d_out)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), batch)
+    for u in range(5):
+        single = api.fbank(pcm[off[u]:off[u + 1]])
+        assert np.array_equal(single, batch[u * 98:(u + 1) * 98])
+
+
+def test_cmvn_kaldi_golden(golden):
+    """test/cmvn_test.cc:38-79: online CMVN of the Kaldi fbank vs apply-cmvn-online, 1e-4."""
+    out = api.cmvn(golden["cmvn_stats"], golden["kaldi_fbank"])
+    assert np.abs(out - golden["kaldi_cmvn"]).max() < 1e-4
+
+
+def test_cmvn_bit_exact_vs_reference_vectors(golden):
+    """700 frames (past the 600-frame window): the fp32 chain is replayed exactly."""
+    out = api.cmvn(golden["cmvn_stats"], golden["ref"]["cmvn_in_700"])
+    assert np.array_equal(out, golden["ref"]["cmvn_out_700"])
+
+
+def test_cmvn_ragged_batch_bit_exact_vs_oracle(port, golden):
+    rng = np.random.default_rng(11)
+    sizes = [1, 0, 599, 600, 601, 1300, 47]
+    feats = (14.0 + 3.0 * rng.standard_normal((sum(sizes), 40))).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    out = api.cmvn(golden["cmvn_stats"], feats, off)
+    for u, n in enumerate(sizes):
+        if n:
+            want = port.cmvn(golden["cmvn_stats"], feats[off[u]:off[u + 1]])
+            assert np.array_equal(out[off[u]:off[u + 1]], want), n
+
+
+def test_cmvn_in_place_on_device(golden, port):
+    import torch
+    rng = np.random.default_rng(12)
+    feats = (14.0 + 3.0 * rng.standard_normal((900, 40))).astype(np.float32)
+    d = torch.from_numpy(feats).cuda()
+    api.cmvn(golden["cmvn_stats"], d, out=d)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), port.cmvn(golden["cmvn_stats"], feats))
+
+
+def test_full_size_properties():
+    """Config-2 shape at a size the oracle cannot finish quickly: 64 x 10 s utterances.
+    Properties: shape, finiteness, batch == shifted copies (time-shift by one frame shift moves
+    the features by exactly one row)."""
+    pcm, off = synth.synth_batch(64, 160000)
+    fb = api.fbank(pcm, off)
+    assert fb.shape == (64 * 998, 40) and np.isfinite(fb).all()
+    shifted = api.fbank(pcm[160:160000])
+    assert np.array_equal(shifted, fb[1:998][:shifted.shape[0]])
