@@ -24,8 +24,9 @@ EXPORTS = [
     "ce_gpu_model_load_config", "ce_gpu_model_free", "ce_gpu_model_info", "ce_gpu_frame_offsets",
     "ce_gpu_fbank", "ce_gpu_cmvn", "ce_gpu_rfft512", "ce_gpu_nnet", "ce_gpu_forward",
     "ce_gpu_nnet_keep_acc", "ce_gpu_nnet_get_acc", "ce_gpu_quantize", "ce_gpu_gemm_u8",
-    "ce_gpu_gemm_f32", "ce_gpu_launch_count",
+    "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
 ]
+PROFILE_CATEGORIES = ["fbank", "cmvn", "gemm", "quantize", "finalize", "other"]
 
 
 class CeGpuError(RuntimeError):
@@ -68,6 +69,8 @@ def lib():
     L.ce_gpu_gemm_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]
     L.ce_gpu_launch_count.restype = C.c_int64
     L.ce_gpu_launch_count.argtypes = [C.c_int]
+    L.ce_gpu_profile_enable.argtypes = [C.c_int]
+    L.ce_gpu_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -114,6 +117,18 @@ def device_count():
 
 def launch_count(reset=False):
     return lib().ce_gpu_launch_count(1 if reset else 0)
+
+
+def profile_enable(on=True):
+    _check(lib().ce_gpu_profile_enable(1 if on else 0), "ce_gpu_profile_enable")
+
+
+def profile_read():
+    """{category: (milliseconds, launches)} of the kernels recorded since the last read."""
+    ms = (C.c_double * 6)()
+    n = (C.c_int64 * 6)()
+    _check(lib().ce_gpu_profile_read(ms, n), "ce_gpu_profile_read")
+    return {k: (ms[i], n[i]) for i, k in enumerate(PROFILE_CATEGORIES)}
 
 
 def frame_offsets(sample_offsets):

@@ -72,6 +72,19 @@ int64_t ce_gpu_launch_count(int reset) {
   return v;
 }
 
+int ce_gpu_profile_enable(int on) {
+  ProfEnable(on != 0);
+  return CE_GPU_OK;
+}
+
+int ce_gpu_profile_read(double *ms, int64_t *launches) {
+  if (!ms || !launches) {
+    SetError("ce_gpu_profile_read: null output");
+    return CE_GPU_EINVAL;
+  }
+  return ProfRead(ms, launches);
+}
+
 // ---- model ----------------------------------------------------------------------------
 
 ce_gpu_model_t *ce_gpu_model_load(const char *nnet_path, const char *prior_path,

@@ -153,6 +153,7 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
   CE_CHECK(utts->Upload(bytes, s));
   const int64_t n_threads = (int64_t)n_utts * num_mel;
   const unsigned grid = (unsigned)((n_threads + 255) / 256);
+  ProfScope prof(kProfCmvn, s);
   cmvn_kernel<<<grid, 256, 0, s>>>(global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(),
                                      n_utts, num_mel, pad_left, pad_right, out_dev, out_stride);
   CE_LAUNCHED();

@@ -21,6 +21,71 @@ const char *LastError() { return g_error; }
 void ClearError() { g_error[0] = '\0'; }
 int64_t &LaunchCounter() { return g_launches; }
 
+namespace {
+struct ProfRec {
+  int cat;
+  cudaEvent_t e0, e1;
+  int64_t launches_before;
+  int64_t launches;
+};
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof_recs;
+thread_local std::vector<cudaEvent_t> g_prof_pool;
+thread_local int g_prof_depth = 0;
+
+cudaEvent_t ProfEvent() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void ProfEnable(bool on) { g_prof_on = on; }
+
+void ProfBegin(int cat, cudaStream_t s) {
+  if (!g_prof_on) return;
+  if (g_prof_depth++ > 0) return;                        // nested scopes: the outermost one counts
+  ProfRec r;
+  r.cat = cat;
+  r.e0 = ProfEvent();
+  r.e1 = ProfEvent();
+  r.launches_before = g_launches;
+  r.launches = 0;
+  cudaEventRecord(r.e0, s);
+  g_prof_recs.push_back(r);
+}
+
+void ProfEnd(cudaStream_t s) {
+  if (!g_prof_on || g_prof_depth == 0) return;
+  if (--g_prof_depth > 0) return;
+  ProfRec &r = g_prof_recs.back();
+  r.launches = g_launches - r.launches_before;
+  cudaEventRecord(r.e1, s);
+}
+
+int ProfRead(double *ms, int64_t *launches) {
+  for (int i = 0; i < kProfNum; ++i) {
+    ms[i] = 0.0;
+    launches[i] = 0;
+  }
+  for (ProfRec &r : g_prof_recs) {
+    CE_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.0f;
+    CE_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.cat] += t;
+    launches[r.cat] += r.launches;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  return CE_GPU_OK;
+}
+
 int DeviceCount() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -49,6 +49,19 @@ int DeviceCount();
     }                                                                              \
   } while (0)
 
+// -- optional per-category kernel timing (ce_gpu_profile_*) ------------------------------------
+enum ProfCat { kProfFbank = 0, kProfCmvn, kProfGemm, kProfQuantize, kProfFinalize, kProfOther, kProfNum };
+void ProfBegin(int cat, cudaStream_t s);
+void ProfEnd(cudaStream_t s);
+struct ProfScope {   // CUDA events around the launches made while it is alive (when enabled)
+  cudaStream_t s;
+  ProfScope(int cat, cudaStream_t stream) : s(stream) { ProfBegin(cat, s); }
+  ~ProfScope() { ProfEnd(s); }
+};
+void ProfEnable(bool on);
+// Waits for the recorded launches, adds their times (ms) and counts per category, clears them.
+int ProfRead(double *ms, int64_t *launches);
+
 // -- device selection -----------------------------------------------------------
 // Makes `device` current; fails with CE_GPU_ENODEVICE when there is none / not sm_100.
 int UseDevice(int device);

@@ -521,6 +521,7 @@ int FbankLaunch(const int16_t *pcm_dev, int64_t total_samples, const int64_t *sa
     CE_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     configured_smem = L.total;
   }
+  ProfScope prof(kProfFbank, s);
   fbank_kernel<<<(unsigned)n_chunks, kThreads, L.total, s>>>(
       pcm_dev, total_samples, chunks->dev<ChunkDesc>(), dt.dev, num_mel, feats_dev, out_row_stride);
   CE_LAUNCHED();

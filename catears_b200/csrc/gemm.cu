@@ -545,6 +545,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   if (tiles <= 0) return CE_GPU_OK;
   const int sms = dev < 64 ? sm_count[dev] : 148;
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+  ProfScope prof(kProfGemm, s);
   gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma0, ma1, mb0, mb1, args);
   CE_LAUNCHED();
   return CE_GPU_OK;

@@ -206,6 +206,7 @@ finalize_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
 
 int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s) {
   if (n <= 0) return CE_GPU_OK;
+  ProfScope prof(kProfQuantize, s);
   init_minmax_kernel<<<(n + 255) / 256, 256, 0, s>>>(mm, n);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -214,6 +215,7 @@ int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s) {
 int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_utt,
                  const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s) {
   if (M <= 0) return CE_GPU_OK;
+  ProfScope prof(kProfQuantize, s);
   minmax_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld, C, M, tile_utt, utts, use, minmax);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -221,6 +223,7 @@ int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_u
 
 int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s) {
   if (n <= 0) return CE_GPU_OK;
+  ProfScope prof(kProfQuantize, s);
   qparams_kernel<<<(n + 127) / 128, 128, 0, s>>>(minmax, q, n);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -233,6 +236,7 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
     SetError("QuantizeLaunch: c_pad %d is not a multiple of 4", c_pad);
     return CE_GPU_EINVAL;
   }
+  ProfScope prof(kProfQuantize, s);
   quantize_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -243,6 +247,7 @@ int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
   if (M <= 0) return CE_GPU_OK;
   const int64_t n = M * c_pad;
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  ProfScope prof(kProfOther, s);
   convert_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, out_bf16, out_hi, out_lo);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -253,6 +258,7 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
                    bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
                    int32_t *argmax, cudaStream_t s) {
   if (M <= 0) return CE_GPU_OK;
+  ProfScope prof(kProfFinalize, s);
   finalize_kernel<<<(M + 7) / 8, 256, 0, s>>>(logits, ld, N, M, tile_utt, utts, out_row_off, left,
                                              right, log_softmax ? 1 : 0, log_prior, loglik, ld_out,
                                              argmax);
