@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds per second of the fbank + CMVN + acoustic-model path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision int8|bf16|tf32|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's own CPU path, same metric
+
+One step = one pass of the whole hot path (ce_gpu_forward: int16 PCM -> 40-mel fbank -> online
+CMVN -> TDNN 6x1024 + 3072 pdfs -> log-likelihoods + argmax) over one batch of synthetic 10 s
+utterances (4096 utterances over 8 GPUs = 512 per GPU; weak scaling, no
+collective on the data path).  `value` is timed with the PCM already in HBM; `e2e` goes through
+the C ABI with pinned HOST buffers (PCM H2D and the per-frame argmax D2H inside the timed region;
+the 12 KB/frame log-likelihood matrix stays in HBM, SURVEY H6 -- `e2e_loglik` also copies it out).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/sec (RTFx) fbank+CMVN+AM"
+UNIT = "audio-s/s"
+UTT_SECONDS = 10.0
+FLOPS_PER_FRAME = 38158336          # 2*(200*1024 + 5*3072*1024 + 1024*3072)
+FBANK_BYTES_PER_FRAME = 480         # 160 samples * 2 B + 40 mel * 4 B
+
+
+def workload_config(utts_per_gpu, world, precision):
+    frames = world * utts_per_gpu * 998
+    return {"workload": "config 3 pipeline: %d synthetic 10 s 16 kHz utterances per GPU (%d in all), "
+                        "40-mel fbank + online CMVN + TDNN 6x1024 (+splice) + 3072 pdfs, %s GEMMs"
+                        % (utts_per_gpu, world * utts_per_gpu, precision),
+            "frames_per_step": frames, "parallelism": "utterances sharded, no collective",
+            "l2": "inputs larger than L2 (%.0f MB PCM + %.1f GB activations per GPU per step)"
+                  % (utts_per_gpu * 0.32, utts_per_gpu * 998 * 8192 / 1e9)}
+
+
+def model_dir():
+    d = os.path.join(tempfile.gettempdir(), "ce_bench_model_%d" % os.getuid())
+    from catears_b200 import synth
+    conf = os.path.join(d, "tdnn.conf")
+    if not os.path.exists(conf):
+        tmp = d + ".tmp%d" % os.getpid()
+        synth.write_model(tmp, name="tdnn", cmvn_stats=synth.default_cmvn_stats())
+        try:
+            os.rename(tmp, d)
+        except OSError:
+            pass                     # another rank won the race
+    return d
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the reference's own implementation (oracle/_ref) or the oracle port
+# ------------------------------------------------------------------------------------------
+
+_W = {}
+
+
+def _cpu_worker_init(conf, kind):
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from catears_b200 import formats as F, synth
+    _W["stats"] = synth.default_cmvn_stats()
+    _W["kind"] = kind
+    if kind == "reference":
+        import ctypes as C
+        from oracle import ref as R
+        r = R.Ref()
+        _W["blas"] = "openblas" if r.set_sgemm("openblas") else "inorder"
+        if _W["blas"] == "inorder":
+            r.set_sgemm("inorder")
+        _W["ref"] = r
+        _W["am"] = r.L.ref_am_open(conf.encode())
+        if not _W["am"]:
+            raise RuntimeError("ref_am_open failed")
+        _W["npdf"] = r.L.ref_am_num_pdfs(_W["am"])
+    else:
+        from oracle.port import Port
+        d = os.path.dirname(conf)
+        _W["port"] = Port()
+        _W["nnet"] = os.path.join(d, "tdnn.nnet")
+        _W["prior"] = F.read_vector(os.path.join(d, "tdnn.prior"))
+        _W["blas"] = "port-inorder"
+
+
+def _cpu_one_utt(u):
+    """fbank -> CMVN -> AM log-likelihoods of synthetic utterance u on one core."""
+    import ctypes as C
+    from catears_b200 import synth
+    pcm = synth.synth_utterance(u)
+    t0 = time.perf_counter()
+    if _W["kind"] == "reference":
+        r = _W["ref"]
+        feats = r.cmvn(_W["stats"], r.fbank(pcm))
+        out = np.zeros((feats.shape[0] + 1, _W["npdf"]), np.float32)
+        cols = C.c_int()
+        n = r.L.ref_am_forward(_W["am"], feats, feats.shape[0], feats.shape[1], out, out.shape[0],
+                               C.byref(cols))
+        assert n == feats.shape[0], n
+    else:
+        p = _W["port"]
+        feats = p.cmvn(_W["stats"], p.fbank(pcm))
+        p.am_forward(_W["nnet"], _W["prior"], 13, 13, feats)
+    return time.perf_counter() - t0, _W["blas"]
+
+
+def _cpu_worker_loop(args):
+    """Runs utterances for at least `budget` seconds; returns (n, elapsed, blas)."""
+    first, budget = args
+    n, t, blas = 0, 0.0, ""
+    while n == 0 or t < budget:
+        dt, blas = _cpu_one_utt(first + n)
+        t += dt
+        n += 1
+    return n, t, blas
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_kind():
+    from oracle import ref as R
+    return "reference" if R.available() else "port"
+
+
+def make_pool(conf, kind, cores):
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(conf, kind))
+
+
+def cpu_baseline(conf, budget_s=6.0):
+    """Bounded sample of the same workload on the host cores (utterance-parallel, one
+    single-threaded worker per core)."""
+    kind, cores = cpu_kind(), cpu_cores()
+    pool = make_pool(conf, kind, cores)
+    try:
+        res = pool.map(_cpu_worker_loop, [(100000 + 64 * i, budget_s) for i in range(cores)])
+    finally:
+        pool.close()
+        pool.join()
+    n = sum(r[0] for r in res)
+    value = sum(r[0] * UTT_SECONDS / r[1] for r in res)      # concurrent workers: rates add
+    return {"value": round(value, 2), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d synthetic 10 s utterances (>= %.0f s of work per core), float AM "
+                      "(cblas_sgemm = %s), fbank+CMVN+AM per utterance on one core, one worker "
+                      "per core" % (n, budget_s, res[0][2])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    conf = os.path.join(model_dir(), "tdnn.conf")
+    kind, cores = cpu_kind(), cpu_cores()
+    pool = make_pool(conf, kind, cores)
+    try:
+        def step(i):
+            return pool.map(_cpu_one_utt, [200000 + i * cores + j for j in range(cores)])
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        blas = ""
+        for i in range(args.steps):
+            blas = step(args.warmup + i)[0][1]
+        dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    audio = args.steps * cores * UTT_SECONDS
+    value = audio / dt
+    sample = ("each step = %d synthetic 10 s utterances (one per host core), float AM "
+              "(cblas_sgemm = %s)" % (cores, blas))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.utts_per_gpu, args.gpus, args.precision),
+        "cpu_baseline": {"value": round(value, 2), "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(self.NAMES, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [x for x in vis.split(",") if x.strip()]
+        if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    conf = os.path.join(model_dir(), "tdnn.conf")
+
+    # CPU baseline first (fork-based pool must start before CUDA is initialised).
+    base = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        base = cpu_baseline(conf)
+
+    import torch
+    import torch.distributed as dist
+    from catears_b200 import api, synth
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_utts = args.utts_per_gpu
+    n_samples = int(UTT_SECONDS * 16000)
+    pcm_np, off = synth.synth_batch(n_utts, n_samples, first=rank * n_utts)
+    frames = int(api.frame_offsets(off)[-1])
+    model = api.AcousticModelGpu(config=conf, precision=args.precision, device=local_rank)
+
+    h_pcm = torch.from_numpy(pcm_np).pin_memory()
+    d_pcm = h_pcm.cuda(non_blocking=True)
+    d_ll = torch.empty((frames, model.num_pdfs), dtype=torch.float32, device="cuda")
+    d_am = torch.empty(frames, dtype=torch.int32, device="cuda")
+    h_am = torch.empty(frames, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        model.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=stream)
+
+    def step_e2e():
+        model.forward(h_pcm.numpy(), off, loglik=d_ll, argmax=h_am.numpy(), stream=stream)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    audio_per_step = world * n_utts * UTT_SECONDS
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    time.sleep(0.3)
+    api.launch_count(reset=True)
+    api.profile_enable(True)
+    ms = timed(step_device, args.steps)
+    prof = api.profile_read()
+    api.profile_enable(False)
+    launches = api.launch_count()
+    clocks = sampler.stop()
+    value = audio_per_step * args.steps / (ms * 1e-3)
+
+    # e2e: host buffers through the C ABI
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = audio_per_step * args.steps / (ms_e2e * 1e-3)
+
+    e2e_ll = None
+    if args.e2e_loglik and world == 1:
+        h_ll = torch.empty((frames, model.num_pdfs), dtype=torch.float32).pin_memory()
+
+        def step_ll():
+            model.forward(h_pcm.numpy(), off, loglik=h_ll.numpy(), argmax=h_am.numpy(), stream=stream)
+        step_ll()
+        ms_ll = timed(step_ll, max(1, args.steps // 2))
+        e2e_ll = audio_per_step * max(1, args.steps // 2) / (ms_ll * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured" if peaks else "fallback"
+    gemm_ms, gemm_n = prof["gemm"]
+    fb_ms, fb_n = prof["fbank"]
+    flops_step = frames * FLOPS_PER_FRAME          # this rank's share
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get("gemm_%s_dram_bytes_per_launch" % args.precision)
+    achieved = flops_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {
+        "kernel": "gemm_kernel<%s> (tcgen05, %d launches/step)" % (args.precision, gemm_n // max(1, args.steps)),
+        "bound": "tensor", "achieved": round(achieved, 2), "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": round(achieved / tensor_peak, 4), "traffic": traffic,
+        "peak_source": "%s bf16_tflops_sustained (no int8 peak was measured; int8 is nominally 2x bf16)" % peak_src,
+        "algorithmic_flops_per_launch": round(flops_step * args.steps / max(1, gemm_n)),
+        "avg_launch_ms": round(gemm_ms / max(1, gemm_n), 4),
+        "share_of_step": round(gemm_ms / ms, 4),
+    }
+    fb_gbs = frames * FBANK_BYTES_PER_FRAME * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else 0.0
+    roofline_fbank = {"kernel": "fbank_kernel", "bound": "hbm", "achieved": round(fb_gbs, 1),
+                      "peak": hbm_peak, "unit": "GB/s", "frac": round(fb_gbs / hbm_peak, 4),
+                      "avg_launch_ms": round(fb_ms / max(1, fb_n), 4),
+                      "share_of_step": round(fb_ms / ms, 4)}
+    out = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "config": workload_config(n_utts, world, args.precision),
+        "clocks": clocks,
+        "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": int(pcm_np.nbytes) * world,
+                "d2h_bytes_per_step": int(frames * 4) * world,
+                "note": "pinned host PCM in, per-frame argmax out; log-likelihoods stay in HBM (H6)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_fbank": roofline_fbank,
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+    }
+    if e2e_ll is not None:
+        out["e2e_loglik"] = {"value": round(e2e_ll, 1), "unit": UNIT,
+                             "d2h_bytes_per_step": int(frames * (4 + 4 * model.num_pdfs))}
+    if base is not None:
+        out["cpu_baseline"] = base
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="int8", choices=["int8", "bf16", "tf32", "fp32"])
+    ap.add_argument("--utts-per-gpu", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-loglik", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: plain `python bench.py --gpus N` re-launches itself under torchrun
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                                   "--master-port", "29517"] + sys.argv)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

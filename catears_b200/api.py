@@ -25,6 +25,7 @@ EXPORTS = [
     "ce_gpu_fbank", "ce_gpu_cmvn", "ce_gpu_rfft512", "ce_gpu_nnet", "ce_gpu_forward",
     "ce_gpu_nnet_keep_acc", "ce_gpu_nnet_get_acc", "ce_gpu_quantize", "ce_gpu_gemm_u8",
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
+    "ce_gpu_partition", "ce_gpu_time_shards",
 ]
 PROFILE_CATEGORIES = ["fbank", "cmvn", "gemm", "quantize", "finalize", "other"]
 
@@ -69,6 +70,8 @@ def lib():
     L.ce_gpu_gemm_f32.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]
     L.ce_gpu_launch_count.restype = C.c_int64
     L.ce_gpu_launch_count.argtypes = [C.c_int]
+    L.ce_gpu_partition.argtypes = [i64p, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.ce_gpu_time_shards.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, i64p, i64p]
     L.ce_gpu_profile_enable.argtypes = [C.c_int]
     L.ce_gpu_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     _lib = L
@@ -138,6 +141,24 @@ def frame_offsets(sample_offsets):
     _check(lib().ce_gpu_frame_offsets(p, off.size - 1, out.ctypes.data_as(C.POINTER(C.c_int64))),
            "ce_gpu_frame_offsets")
     return out
+
+
+def partition(frame_offsets_, n_parts):
+    """Contiguous, frame-balanced utterance groups, one per GPU: returns part_begin [n_parts+1]."""
+    off, p = _offsets(frame_offsets_)
+    out = np.zeros(n_parts + 1, np.int32)
+    _check(lib().ce_gpu_partition(p, off.size - 1, n_parts, out.ctypes.data_as(C.POINTER(C.c_int32))),
+           "ce_gpu_partition")
+    return out
+
+
+def time_shards(total_frames, n_parts, left_context, right_context, cmvn_history=600):
+    """Long-form time shards with halos: arrays keep_begin, keep_end, feed_begin, feed_end."""
+    arrs = [np.zeros(n_parts, np.int64) for _ in range(4)]
+    ptrs = [a.ctypes.data_as(C.POINTER(C.c_int64)) for a in arrs]
+    _check(lib().ce_gpu_time_shards(total_frames, n_parts, left_context, right_context, cmvn_history, *ptrs),
+           "ce_gpu_time_shards")
+    return arrs
 
 
 def fbank(pcm, sample_offsets=None, num_mel=40, out=None, device=0, stream=None):

@@ -366,6 +366,50 @@ int ce_gpu_nnet_get_acc(ce_gpu_model_t *m, int utt, int32_t *acc, int64_t cap, i
   return CE_GPU_OK;
 }
 
+// ---- multi-GPU planning ---------------------------------------------------------------------
+
+int ce_gpu_partition(const int64_t *utt_frame_offsets, int n_utts, int n_parts, int32_t *part_begin) {
+  CE_CHECK(CheckOffsets(utt_frame_offsets, n_utts, "ce_gpu_partition"));
+  if (n_parts < 1 || !part_begin) {
+    SetError("ce_gpu_partition: bad arguments");
+    return CE_GPU_EINVAL;
+  }
+  const int64_t base = n_utts > 0 ? utt_frame_offsets[0] : 0;
+  const int64_t total = n_utts > 0 ? utt_frame_offsets[n_utts] - base : 0;
+  part_begin[0] = 0;
+  int u = 0;
+  for (int p = 1; p < n_parts; ++p) {
+    // first utterance boundary at or after the ideal cut p/n of the frames (ties: earlier)
+    const int64_t cut = base + (total * p + n_parts / 2) / n_parts;
+    while (u < n_utts && utt_frame_offsets[u] < cut) {
+      // step to the boundary nearest to the cut
+      if (utt_frame_offsets[u + 1] - cut > cut - utt_frame_offsets[u]) break;
+      ++u;
+    }
+    part_begin[p] = u;
+  }
+  part_begin[n_parts] = n_utts;
+  return CE_GPU_OK;
+}
+
+int ce_gpu_time_shards(int64_t total_frames, int n_parts, int left_context, int right_context,
+                       int cmvn_history, int64_t *keep_begin, int64_t *keep_end,
+                       int64_t *feed_begin, int64_t *feed_end) {
+  if (total_frames < 0 || n_parts < 1 || left_context < 0 || right_context < 0 || cmvn_history < 0 ||
+      !keep_begin || !keep_end || !feed_begin || !feed_end) {
+    SetError("ce_gpu_time_shards: bad arguments");
+    return CE_GPU_EINVAL;
+  }
+  for (int p = 0; p < n_parts; ++p) {
+    keep_begin[p] = total_frames * p / n_parts;
+    keep_end[p] = total_frames * (p + 1) / n_parts;
+    feed_begin[p] = std::max<int64_t>(0, keep_begin[p] - left_context - cmvn_history);
+    feed_end[p] = std::min<int64_t>(total_frames, keep_end[p] + right_context);
+    if (keep_end[p] == keep_begin[p]) feed_begin[p] = feed_end[p] = keep_begin[p];
+  }
+  return CE_GPU_OK;
+}
+
 // ---- matrix level -----------------------------------------------------------------------
 
 int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, float *scale,

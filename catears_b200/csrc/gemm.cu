@@ -32,18 +32,22 @@
 namespace ce {
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB
 constexpr int kBBytes = kTileN * kTileKBytes;            // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kThreads = 192;
-constexpr int kEpiWarps = 4;
-constexpr int kStagePitch = 36;                          // floats per staged row (32 + 4 pad)
-constexpr int kEpiStageBytes = 32 * kStagePitch * 4;     // per epilogue warp
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes +
-                           kEpiWarps * kEpiStageBytes + 256 /*barriers*/;
+constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quadrant (column halves)
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 64 + kEpiThreads;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
+constexpr int kParamBytes = 4 * kTileN * 4;              // bias, bn scale, bn offset, int correction
+constexpr int kOffStage = kStages * kStageBytes;         // output staging (1024-aligned)
+constexpr int kOffParams = kOffStage + kEpiWarps * kOutTileBytes;
+constexpr int kOffBars = kOffParams + kParamBytes;
+constexpr int kSmemBytes = 1024 /*alignment slack*/ + kOffBars + 256;
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -90,6 +94,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       :
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {   // smem of all my stores has been read
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() {               // the 256 epilogue threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() {
@@ -173,20 +197,77 @@ __device__ __forceinline__ float round_tf32(float v) {
 }
 
 // ---------------------------------------------------------------------------
+// epilogue math: 32 accumulator columns of one row, reference order of operations
+// ---------------------------------------------------------------------------
+struct RowConst {
+  int32_t row_corr;     // zp_b * sum_k A[row][k]   (u8 path)
+  float c_scale;        // scale_a * scale_b          (u8 path)
+};
+
+template <int KIND, bool RELU, bool BN, bool MM>
+__device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[32], const float *sp,
+                                         int pcol, const RowConst rc, float &vmin, float &vmax) {
+  const float4 *b4 = reinterpret_cast<const float4 *>(sp + pcol);
+  const float4 *s4 = reinterpret_cast<const float4 *>(sp + kTileN + pcol);
+  const float4 *o4 = reinterpret_cast<const float4 *>(sp + 2 * kTileN + pcol);
+  const int4 *c4 = reinterpret_cast<const int4 *>(sp + 3 * kTileN + pcol);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bb = b4[q];
+    float4 ss = make_float4(1.f, 1.f, 1.f, 1.f), oo = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BN) {
+      ss = s4[q];
+      oo = o4[q];
+    }
+    int4 cc = make_int4(0, 0, 0, 0);
+    if (KIND == kKindI8) cc = c4[q];
+    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+    const float sv[4] = {ss.x, ss.y, ss.z, ss.w};
+    const float ov[4] = {oo.x, oo.y, oo.z, oo.w};
+    const int cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * q + e;
+      float x;
+      if (KIND == kKindI8) {
+        // acc = sum (A - zpA)(B - zpB) = raw - zpB*rowsum(A) - zpA*colsum(B) + K*zpA*zpB
+        const int32_t a = (int32_t)raw[j] + (cv[e] - rc.row_corr);
+        x = __fmul_rn(__int2float_rn(a), rc.c_scale);                 // eight_bit_int_gemm.cc:389
+      } else {
+        x = __uint_as_float(raw[j]);
+      }
+      x = __fadd_rn(x, bv[e]);                                         // nnet.cc:34
+      if (RELU) x = (x < 0.0f) ? 0.0f : x;                             // nnet.cc:156
+      if (BN) {
+        x = __fmul_rn(x, sv[e]);                                       // nnet.cc:114
+        x = __fadd_rn(x, ov[e]);                                       // nnet.cc:115
+      }
+      if (MM) {
+        vmin = fminf(vmin, x);                                         // NaNs ignored, as the
+        vmax = fmaxf(vmax, x);                                         // comparisons of matrix.cc:337-340
+      }
+      v[j] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
+            const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
             const GemmArgs p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *smem_a = smem;                                   // [kStages][kABytes]
   unsigned char *smem_b = smem + kStages * kABytes;               // [kStages][kBBytes]
-  float *epi_stage = reinterpret_cast<float *>(smem + kStages * kStageBytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes + kEpiWarps * kEpiStageBytes);
+  unsigned char *smem_out = smem + kOffStage;                     // [kEpiWarps][kOutTileBytes]
+  float *sp = reinterpret_cast<float *>(smem + kOffParams);       // [4][kTileN]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + kStages);
@@ -295,9 +376,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
-    float *stg = epi_stage + (warp - 2) * (32 * kStagePitch);
+    const int half = ew >> 2;                            // which 128 of the tile's 256 columns
+    const int et = threadIdx.x - 64;                     // 0..255
+    unsigned char *stg = smem_out + ew * kOutTileBytes;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int flags = (p.relu ? 1 : 0) | (p.bn_scale ? 2 : 0) | (p.minmax ? 4 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -306,23 +392,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * kTileN;
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
 
-      // ---- per-tile / per-row constants ----
+      // ---- per-tile constants; per-column parameters -> shared memory ----
       const int utt = p.tile_utt ? p.tile_utt[m_tile] : 0;
       int32_t zp_a = 0;
-      float c_scale = 1.0f;
-      int32_t row_corr = 0;                              // zp_b * sum_k A[row][k]
+      RowConst rc;
+      rc.row_corr = 0;
+      rc.c_scale = 1.0f;
       int32_t kzz = 0;
       if (KIND == kKindI8) {
         const QParam q = p.qa[utt];
         zp_a = q.zero_point;
-        c_scale = __fmul_rn(q.scale, p.scale_b);         // matrix.cc:403 (float * float)
+        rc.c_scale = __fmul_rn(q.scale, p.scale_b);      // matrix.cc:403 (float * float)
+        kzz = p.k_true * zp_a * p.zp_b;
+      }
+      epi_bar();                                         // previous tile's parameters are no longer read
+      {
+        const int col = n0 + et;                         // parameter arrays are padded to kTileN
+        sp[et] = p.bias ? __ldg(p.bias + col) : 0.0f;
+        sp[kTileN + et] = p.bn_scale ? __ldg(p.bn_scale + col) : 1.0f;
+        sp[2 * kTileN + et] = p.bn_offset ? __ldg(p.bn_offset + col) : 0.0f;
+        int32_t corr = 0;
+        if (KIND == kKindI8) corr = kzz - zp_a * __ldg(p.b_colsum + col);
+        reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = corr;
+      }
+      if (KIND == kKindI8) {
         int32_t rs = 0;
         for (int t = 0; t < p.n_taps; ++t) {
           const int r = my_row + p.tap_off[t];
-          if (r >= 0 && r < p.M) rs += p.a_rowsum[r];
+          if (r >= 0 && r < p.M) rs += __ldg(p.a_rowsum + r);
         }
-        row_corr = p.zp_b * rs;
-        kzz = p.k_true * zp_a * p.zp_b;
+        rc.row_corr = p.zp_b * rs;
       }
       bool use_row = false;                              // takes part in the fused FindMinMax
       if (p.minmax) {
@@ -344,96 +443,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
       }
       float vmin = FLT_MAX, vmax = -FLT_MAX;
+      epi_bar();                                         // parameters visible to all epilogue warps
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * 128);
 
-      for (int c = 0; c < kTileN / 32; ++c) {
-        const int col0 = n0 + c * 32;
+      for (int c = 0; c < 4; ++c) {
+        const int pcol = half * 128 + c * 32;            // column within the tile
+        const int col0 = n0 + pcol;
         if (col0 >= p.n_store) break;                    // warp-uniform
         uint32_t raw[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), raw);
         float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float x;
-          if (KIND == kKindI8) {
-            // acc = sum (A - zpA)(B - zpB) = raw - zpB*rowsum(A) - zpA*colsum(B) + K*zpA*zpB
-            const int32_t a = (int32_t)raw[j] - row_corr - zp_a * __ldg(p.b_colsum + col) + kzz;
-            if (p.out_acc && my_row < p.M && col < p.N) p.out_acc[(int64_t)my_row * p.ld_out + col] = a;
-            x = __fmul_rn(__int2float_rn(a), c_scale);   // eight_bit_int_gemm.cc:389
-          } else {
-            x = __uint_as_float(raw[j]);
-          }
-          if (p.bias) x = __fadd_rn(x, __ldg(p.bias + col));                       // nnet.cc:34
-          if (p.relu) x = (x < 0.0f) ? 0.0f : x;                                     // nnet.cc:156
-          if (p.bn_scale) {
-            x = __fmul_rn(x, __ldg(p.bn_scale + col));                               // nnet.cc:114
-            x = __fadd_rn(x, __ldg(p.bn_offset + col));                              // nnet.cc:115
-          }
-          if (col >= p.N) x = 0.0f;                      // K padding of the next layer
-          if (use_row && col < p.N) {
-            vmin = (x < vmin) ? x : vmin;                // comparisons as matrix.cc:337-340
-            vmax = (x > vmax) ? x : vmax;
-          }
-          v[j] = x;
+        float cmin = FLT_MAX, cmax = -FLT_MAX;           // this chunk's share of FindMinMax
+        switch (flags) {
+          case 0: epi_math<KIND, false, false, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 1: epi_math<KIND, true, false, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 2: epi_math<KIND, false, true, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 3: epi_math<KIND, true, true, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 4: epi_math<KIND, false, false, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 5: epi_math<KIND, true, false, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 6: epi_math<KIND, false, true, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          default: epi_math<KIND, true, true, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
         }
-        // ---- transpose through shared memory: thread = row  ->  8 lanes = one 128-byte row ----
+        if (col0 + 32 > p.N || p.out_acc) {              // rare: ragged N, or the debug dump
+          cmin = FLT_MAX;
+          cmax = -FLT_MAX;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          *reinterpret_cast<float4 *>(stg + lane * kStagePitch + 4 * j) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        __syncwarp();
-        const int sub = lane >> 3;                       // row within a group of 4
-        const int cc = (lane & 7) * 4;                   // column within the 32-wide chunk
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub;
-          const int grow = m0 + quad * 32 + r;
-          const int gcol = col0 + cc;
-          const float4 f = *reinterpret_cast<const float4 *>(stg + r * kStagePitch + cc);
-          if (grow < p.M && gcol < p.n_store) {
-            const int64_t o = (int64_t)grow * p.ld_out + gcol;
-            const bool full = gcol + 4 <= p.n_store;
-            const float e[4] = {f.x, f.y, f.z, f.w};
-            if (p.out_bf16) {
-              if (full) {
-                __nv_bfloat162 lo2 = __floats2bfloat162_rn(f.x, f.y);
-                __nv_bfloat162 hi2 = __floats2bfloat162_rn(f.z, f.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<uint32_t *>(&lo2);
-                pk.y = *reinterpret_cast<uint32_t *>(&hi2);
-                *reinterpret_cast<uint2 *>(p.out_bf16 + o) = pk;
-              } else {
-                for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_bf16[o + q] = __float2bfloat16_rn(e[q]);
-              }
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (KIND == kKindI8 && p.out_acc && my_row < p.M && col < p.N) {
+              const int32_t cj = reinterpret_cast<const int32_t *>(sp)[3 * kTileN + pcol + j];
+              p.out_acc[(int64_t)my_row * p.ld_out + col] = (int32_t)raw[j] + (cj - rc.row_corr);
             }
-            if (p.out_f32) {
-              float h[4] = {e[0], e[1], e[2], e[3]};
-              if (p.round_tf32) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) h[q] = round_tf32(e[q]);
-              }
-              if (full) {
-                *reinterpret_cast<float4 *>(p.out_f32 + o) = make_float4(h[0], h[1], h[2], h[3]);
-              } else {
-                for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_f32[o + q] = h[q];
-              }
-              if (p.out_lo) {
-                if (full) {
-                  *reinterpret_cast<float4 *>(p.out_lo + o) =
-                      make_float4(e[0] - h[0], e[1] - h[1], e[2] - h[2], e[3] - h[3]);
-                } else {
-                  for (int q = 0; q < 4 && gcol + q < p.n_store; ++q) p.out_lo[o + q] = e[q] - h[q];
-                }
-              }
+            if (col >= p.N) {
+              v[j] = 0.0f;                               // K padding of the next layer
+            } else {
+              cmin = fminf(cmin, v[j]);
+              cmax = fmaxf(cmax, v[j]);
             }
           }
         }
-        __syncwarp();
+        vmin = fminf(vmin, cmin);
+        vmax = fmaxf(vmax, cmax);
+
+        // ---- registers -> swizzled staging tile -> one TMA store per 32 x 128 B ----
+        const int sw = lane & 7;
+        if (KIND == kKindBF16 && p.out_bf16) {
+          if ((c & 1) == 0) {                            // a new 64-column tile: previous store must
+            if (lane == 0) tma_store_wait_read();        // have finished reading the buffer
+            __syncwarp();
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            const int piece = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4 *>(stg + lane * 128 + ((piece ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          const bool flush = (c & 1) == 1 || col0 + 32 >= p.n_store;
+          if (flush) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&map_o0, stg_u32, col0 - (c & 1) * 32, m0 + quad * 32);
+          }
+        } else {
+          float h[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) h[j] = p.round_tf32 ? round_tf32(v[j]) : v[j];
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            *reinterpret_cast<float4 *>(stg + lane * 128 + ((q ^ sw) << 4)) =
+                make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&map_o0, stg_u32, col0, m0 + quad * 32);
+          if (p.out_lo) {                                // 3xTF32 consumers: the exact remainder
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              *reinterpret_cast<float4 *>(stg + lane * 128 + ((q ^ sw) << 4)) =
+                  make_float4(v[4 * q] - h[4 * q], v[4 * q + 1] - h[4 * q + 1], v[4 * q + 2] - h[4 * q + 2],
+                              v[4 * q + 3] - h[4 * q + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&map_o1, stg_u32, col0, m0 + quad * 32);
+          }
+        }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
@@ -445,6 +551,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
 
       if (p.minmax) {
+        if (!use_row) {
+          vmin = FLT_MAX;
+          vmax = -FLT_MAX;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
@@ -456,6 +566,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
       }
     }
+    if (lane == 0) tma_store_wait_all();                 // global writes done before the CTA exits
   }
 
   tc_fence_before();
@@ -521,9 +632,48 @@ int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows
   return CE_GPU_OK;
 }
 
+// 2-D map for the TMA stores of the epilogue: [rows x cols] window of a row-major matrix with row
+// stride ld (elements), box = 32 rows x 128 bytes, 128B swizzle.
+int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap *map) {
+  EncodeTiledFn fn;
+  CE_CHECK(GetEncodeFn(&fn));
+  const int elt = bf16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elt) % 16 != 0) {
+    SetError("GEMM output is not 16-byte aligned (base %p, row pitch %lld bytes)", base,
+             (long long)(ld * elt));
+    return CE_GPU_EINVAL;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * elt)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elt), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    SetError("cuTensorMapEncodeTiled (output) failed with CUresult %d (rows %lld cols %lld ld %lld)",
+             (int)r, (long long)rows, (long long)cols, (long long)ld);
+    return CE_GPU_ECUDA;
+  }
+  return CE_GPU_OK;
+}
+
 template <int KIND>
 int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
-  CUtensorMap ma0, ma1, mb0, mb1;
+  CUtensorMap ma0, ma1, mb0, mb1, mo0, mo1;
+  const bool out_is_bf16 = (KIND == kKindBF16) && args.out_bf16 != nullptr;
+  const void *o0 = out_is_bf16 ? static_cast<const void *>(args.out_bf16) : static_cast<const void *>(args.out_f32);
+  if (o0 == nullptr) {
+    SetError("GemmLaunch: no output buffer");
+    return CE_GPU_EINVAL;
+  }
+  CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M, args.n_store, args.ld_out, &mo0));
+  if (args.out_lo) {
+    CE_CHECK(MakeOutMap(false, args.out_lo, args.M, args.n_store, args.ld_out, &mo1));
+  } else {
+    mo1 = mo0;                                           // never used by the kernel
+  }
   CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
   CE_CHECK(MakeMap(KIND, ops.a[1] ? ops.a[1] : ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma1));
   CE_CHECK(MakeMap(KIND, ops.b[0], ops.rows_b, ops.k_total, kTileN, &mb0));
@@ -546,7 +696,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   const int sms = dev < 64 ? sm_count[dev] : 148;
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
   ProfScope prof(kProfGemm, s);
-  gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma0, ma1, mb0, mb1, args);
+  gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma0, ma1, mb0, mb1, mo0, mo1, args);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

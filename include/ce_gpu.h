@@ -148,6 +148,22 @@ int ce_gpu_gemm_u8(const uint8_t *a, float scale_a, int32_t zp_a, const uint8_t 
 int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *c,
                     int precision, int device, void *stream);
 
+/* ---- multi-GPU planning (host only; utterances are independent, so there is no collective) ---- */
+
+/* Splits n_utts utterances (frame offsets as above) into n_parts CONTIGUOUS groups of nearly
+ * equal frame counts, one per GPU: part p owns utterances [part_begin[p], part_begin[p+1]).
+ * part_begin has n_parts+1 entries.  Deterministic: every rank computes the same plan. */
+int ce_gpu_partition(const int64_t *utt_frame_offsets, int n_utts, int n_parts, int32_t *part_begin);
+
+/* Long-form audio (one stream of total_frames frames) as n_parts contiguous time shards with
+ * recomputed halos: shard p keeps output frames [keep_begin[p], keep_end[p])
+ * and must be fed frames [feed_begin[p], feed_end[p]) = the kept range extended by
+ * left_halo = left_context + cmvn_history frames before and right_context frames after (clipped
+ * to the stream).  Sample range of a frame range [a, b): [160 a, 160 (b-1) + 400). */
+int ce_gpu_time_shards(int64_t total_frames, int n_parts, int left_context, int right_context,
+                       int cmvn_history, int64_t *keep_begin, int64_t *keep_end,
+                       int64_t *feed_begin, int64_t *feed_end);
+
 /* ---- instrumentation -------------------------------------------------------- */
 
 /* Number of kernels this library has launched on this thread since the last reset. */
