@@ -11,7 +11,7 @@
 // exactly the reference's operations (double add, float round; un-fused float multiply/add).
 // Parallelism comes from utterances x bins; the count / smoothing weight / 1/count depend only
 // on the frame index and are taken from a 600-entry table built on the host with the same
-// arithmetic.  Loads are prefetched eight frames ahead; a warp reads 128 contiguous bytes.
+// arithmetic.  Loads run one 16-frame batch ahead of the chain; a warp reads 128 contiguous bytes.
 //
 // HBM traffic: 4*mel bytes read + 4*mel written per frame (x_{t-600} is an L2 hit).
 
@@ -36,7 +36,7 @@ struct CmvnStep {    // frame-index-only part of the chain (t < 600; t >= 599 us
   float nscale;      // -(float)(1 / count_after_smoothing)
 };
 
-constexpr int kUnroll = 8;
+constexpr int kUnroll = 16;
 
 // One thread per (utt, d), flattened so that warps stay full for any mel.
 __global__ void __launch_bounds__(256)
@@ -54,33 +54,46 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   const bool apply = g != nullptr;
   const float gd = apply ? g[d] : 0.0f;
 
+  // Software pipeline: the loads of batch k+1 are in flight while the (sequential, rounding-
+  // exact) chain of batch k runs.
   float cached = 0.0f, y_first = 0.0f, y_last = 0.0f;
-  for (int t0 = 0; t0 < T; t0 += kUnroll) {
-    float xv[kUnroll], xo[kUnroll];
+  float xv[kUnroll], xo[kUnroll];
+  auto load_batch = [&](int t0, float (&a)[kUnroll], float (&b)[kUnroll]) {
 #pragma unroll
     for (int j = 0; j < kUnroll; ++j) {
       const int t = t0 + j;
-      xv[j] = (t < T) ? __ldg(x + (int64_t)t * mel) : 0.0f;
-      xo[j] = (apply && t < T && t >= kCmvnWindow) ? __ldg(x + (int64_t)(t - kCmvnWindow) * mel) : 0.0f;
+      a[j] = (t < T) ? __ldg(x + (int64_t)t * mel) : 0.0f;
+      b[j] = (apply && t < T && t >= kCmvnWindow) ? __ldg(x + (int64_t)(t - kCmvnWindow) * mel) : 0.0f;
+    }
+  };
+  load_batch(0, xv, xo);
+  for (int t0 = 0; t0 < T; t0 += kUnroll) {
+    float nv[kUnroll], no[kUnroll];
+    load_batch(t0 + kUnroll, nv, no);
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int t = t0 + j;
+      if (t < T) {
+        float r = xv[j];
+        if (apply) {
+          double s = (double)cached;                       // cmvn.cc:42-47 (double accumulate)
+          s += (double)xv[j];
+          if (t >= kCmvnWindow) s += -1.0 * (double)xo[j];
+          cached = (float)s;                               // cmvn.cc:63-67 (stored as float)
+          const CmvnStep st = steps[min(t, kCmvnWindow - 1)];
+          float stat = cached;
+          if (t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, gd));   // AddVec
+          r = __fadd_rn(xv[j], __fmul_rn(st.nscale, stat));                          // cmvn.cc:96-97
+        }
+        y[(int64_t)t * out_stride] = r;
+        if (t == 0) y_first = r;
+        y_last = r;
+      }
     }
 #pragma unroll
     for (int j = 0; j < kUnroll; ++j) {
-      const int t = t0 + j;
-      if (t >= T) break;
-      float r = xv[j];
-      if (apply) {
-        double s = (double)cached;                       // cmvn.cc:42-47 (double accumulate)
-        s += (double)xv[j];
-        if (t >= kCmvnWindow) s += -1.0 * (double)xo[j];
-        cached = (float)s;                               // cmvn.cc:63-67 (stored as float)
-        const CmvnStep st = steps[min(t, kCmvnWindow - 1)];
-        float stat = cached;
-        if (t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, gd));   // AddVec
-        r = __fadd_rn(xv[j], __fmul_rn(st.nscale, stat));                          // cmvn.cc:96-97
-      }
-      y[(int64_t)t * out_stride] = r;
-      if (t == 0) y_first = r;
-      y_last = r;
+      xv[j] = nv[j];
+      xo[j] = no[j];
     }
   }
   if (T > 0) {

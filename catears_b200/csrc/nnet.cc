@@ -15,18 +15,28 @@
 
 #include <algorithm>
 
+void ce_gpu_model::ChunkWs::Free() {
+  x0.Free();
+  for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
+  act_u8.Free(); rowsum.Free(); logits.Free(); minmax.Free(); qparams.Free();
+  stage_loglik.Free(); stage_argmax.Free();
+  cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
+  if (stream) cudaStreamDestroy(stream);
+  if (done) cudaEventDestroy(done);
+  stream = nullptr;
+  done = nullptr;
+}
+
 ce_gpu_model::~ce_gpu_model() {
   cudaSetDevice(device);
+  cudaDeviceSynchronize();
   for (auto &b : blocks) {
     b.w[0].Free(); b.w[1].Free(); b.bias.Free(); b.bn_scale.Free(); b.bn_offset.Free(); b.colsum.Free();
   }
   log_prior.Free(); cmvn_dev.Free();
-  stage_pcm.Free(); stage_feats.Free(); stage_loglik.Free(); stage_argmax.Free();
-  feats.Free(); x0.Free();
-  for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
-  act_u8.Free(); rowsum.Free(); logits.Free(); acc_dump.Free(); minmax.Free(); qparams.Free();
-  fbank_chunks.Free(); cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
-  if (own_stream) cudaStreamDestroy(own_stream);
+  stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
+  ws[0].Free(); ws[1].Free();
+  if (inputs_ready) cudaEventDestroy(inputs_ready);
 }
 
 namespace ce {
@@ -170,6 +180,12 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     long v = atol(e);
     if (v >= kTileM) m->max_chunk_rows = v;
   }
+  if (const char *e = getenv("CE_GPU_OVERLAP")) m->overlap = atoi(e) != 0;
+  for (int i = 0; i < 2; ++i) {
+    CE_CUDA(cudaStreamCreateWithFlags(&m->ws[i].stream, cudaStreamNonBlocking));
+    CE_CUDA(cudaEventCreateWithFlags(&m->ws[i].done, cudaEventDisableTiming));
+  }
+  CE_CUDA(cudaEventCreateWithFlags(&m->inputs_ready, cudaEventDisableTiming));
   return CE_GPU_OK;
 }
 
@@ -192,8 +208,9 @@ RowUse MakeRowUse(const ce_gpu_model *m, int producer /* -1 = network input */) 
 
 // Output rows are addressed by absolute frame index (frame_off), so loglik_dev / argmax_dev are
 // the bases of the whole batch's outputs.
-int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
-                 bool apply_cmvn, float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
+int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const float *feats_dev,
+                 const int64_t *frame_off, int n_utts, bool apply_cmvn, float *loglik_dev,
+                 int32_t *argmax_dev, cudaStream_t s) {
   const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
   const int nb = (int)m->blocks.size();
 
@@ -212,12 +229,12 @@ int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_o
   }
   const int M = (int)M64;
   const int m_tiles = M / kTileM;
-  CE_CHECK(m->utt_table.Acquire(sizeof(UttRows) * n_utts));
-  CE_CHECK(m->tile_table.Acquire(sizeof(int32_t) * m_tiles));
-  CE_CHECK(m->outrow_table.Acquire(sizeof(int64_t) * n_utts));
-  UttRows *hu = m->utt_table.host<UttRows>();
-  int32_t *ht = m->tile_table.host<int32_t>();
-  int64_t *ho = m->outrow_table.host<int64_t>();
+  CE_CHECK(w->utt_table.Acquire(sizeof(UttRows) * n_utts));
+  CE_CHECK(w->tile_table.Acquire(sizeof(int32_t) * m_tiles));
+  CE_CHECK(w->outrow_table.Acquire(sizeof(int64_t) * n_utts));
+  UttRows *hu = w->utt_table.host<UttRows>();
+  int32_t *ht = w->tile_table.host<int32_t>();
+  int64_t *ho = w->outrow_table.host<int64_t>();
   for (int u = 0; u < n_utts; ++u) {
     const int64_t T = frame_off[u + 1] - frame_off[u];
     hu[u].row_off = (int32_t)row_off64[u];
@@ -226,54 +243,54 @@ int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_o
     const int64_t end = (u + 1 < n_utts) ? row_off64[u + 1] : M64;
     for (int64_t t = row_off64[u] / kTileM; t < end / kTileM; ++t) ht[t] = u;
   }
-  CE_CHECK(m->utt_table.Upload(sizeof(UttRows) * n_utts, s));
-  CE_CHECK(m->tile_table.Upload(sizeof(int32_t) * m_tiles, s));
-  CE_CHECK(m->outrow_table.Upload(sizeof(int64_t) * n_utts, s));
-  const UttRows *d_utts = m->utt_table.dev<UttRows>();
-  const int32_t *d_tile = m->tile_table.dev<int32_t>();
+  CE_CHECK(w->utt_table.Upload(sizeof(UttRows) * n_utts, s));
+  CE_CHECK(w->tile_table.Upload(sizeof(int32_t) * m_tiles, s));
+  CE_CHECK(w->outrow_table.Upload(sizeof(int64_t) * n_utts, s));
+  const UttRows *d_utts = w->utt_table.dev<UttRows>();
+  const int32_t *d_tile = w->tile_table.dev<int32_t>();
 
   // ---- workspace ----
   int wmax = 4;
   for (const DeviceBlock &D : m->blocks) wmax = std::max(wmax, std::max(D.c_pad, RoundUp(D.meta.out_dim, 4)));
   const int ldp = RoundUp(NP, 4);
-  CE_CHECK(m->x0.Reserve(sizeof(float) * (size_t)M * F));
-  CE_CHECK(m->logits.Reserve(sizeof(float) * (size_t)M * ldp));
+  CE_CHECK(w->x0.Reserve(sizeof(float) * (size_t)M * F));
+  CE_CHECK(w->logits.Reserve(sizeof(float) * (size_t)M * ldp));
   if (m->kind == kKindI8) {
-    CE_CHECK(m->act_f32[0].Reserve(sizeof(float) * (size_t)M * wmax));
-    CE_CHECK(m->act_u8.Reserve((size_t)M * wmax));
-    CE_CHECK(m->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
-    CE_CHECK(m->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
-    CE_CHECK(m->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
+    CE_CHECK(w->act_f32[0].Reserve(sizeof(float) * (size_t)M * wmax));
+    CE_CHECK(w->act_u8.Reserve((size_t)M * wmax));
+    CE_CHECK(w->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
+    CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
+    CE_CHECK(w->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
   } else if (m->kind == kKindBF16) {
-    for (int i = 0; i < 2; ++i) CE_CHECK(m->act_bf16[i].Reserve(2 * (size_t)M * wmax));
+    for (int i = 0; i < 2; ++i) CE_CHECK(w->act_bf16[i].Reserve(2 * (size_t)M * wmax));
   } else {
     for (int i = 0; i < 2; ++i) {
-      CE_CHECK(m->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
-      if (m->n_pass == 3) CE_CHECK(m->act_lo[i].Reserve(sizeof(float) * (size_t)M * wmax));
+      CE_CHECK(w->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
+      if (m->n_pass == 3) CE_CHECK(w->act_lo[i].Reserve(sizeof(float) * (size_t)M * wmax));
     }
   }
 
   // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155 ----
   CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
                       apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, frame_off, row_off64.data(),
-                      n_utts, F, L, R, m->x0.as<float>(), F, &m->cmvn_utts, s));
+                      n_utts, F, L, R, w->x0.as<float>(), F, &w->cmvn_utts, s));
 
   // ---- network input in the operand format of the data path ----
-  uint32_t *mm = m->minmax.as<uint32_t>();
-  QParam *qp = m->qparams.as<QParam>();
+  uint32_t *mm = w->minmax.as<uint32_t>();
+  QParam *qp = w->qparams.as<QParam>();
   const int c0 = m->blocks[0].c_pad;
   if (m->kind == kKindI8) {
     CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
-    CE_CHECK(MinMaxLaunch(m->x0.as<float>(), F, F, M, d_tile, d_utts, MakeRowUse(m, -1), mm, s));
+    CE_CHECK(MinMaxLaunch(w->x0.as<float>(), F, F, M, d_tile, d_utts, MakeRowUse(m, -1), mm, s));
     CE_CHECK(QParamsLaunch(mm, qp, n_utts, s));
-    CE_CHECK(QuantizeLaunch(m->x0.as<float>(), F, F, M, c0, d_tile, qp, m->act_u8.as<uint8_t>(),
-                            m->rowsum.as<int32_t>(), s));
+    CE_CHECK(QuantizeLaunch(w->x0.as<float>(), F, F, M, c0, d_tile, qp, w->act_u8.as<uint8_t>(),
+                            w->rowsum.as<int32_t>(), s));
   } else if (m->kind == kKindBF16) {
-    CE_CHECK(ConvertLaunch(m->x0.as<float>(), F, F, M, c0, m->act_bf16[0].as<__nv_bfloat16>(),
+    CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, w->act_bf16[0].as<__nv_bfloat16>(),
                            nullptr, nullptr, s));
   } else {
-    CE_CHECK(ConvertLaunch(m->x0.as<float>(), F, F, M, c0, nullptr, m->act_f32[0].as<float>(),
-                           m->n_pass == 3 ? m->act_lo[0].as<float>() : nullptr, s));
+    CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, nullptr, w->act_f32[0].as<float>(),
+                           m->n_pass == 3 ? w->act_lo[0].as<float>() : nullptr, s));
   }
 
   m->kept_valid = false;
@@ -311,14 +328,14 @@ int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_o
     const int next_c = last ? 0 : m->blocks[b + 1].c_pad;
 
     if (m->kind == kKindI8) {
-      ops.a[0] = m->act_u8.ptr;
-      a.a_rowsum = m->rowsum.as<int32_t>();
+      ops.a[0] = w->act_u8.ptr;
+      a.a_rowsum = w->rowsum.as<int32_t>();
       a.b_colsum = D.colsum.as<int32_t>();
       a.zp_b = D.zp_b;
       a.scale_b = D.scale_b;
       a.k_true = a.n_taps * D.meta.in_dim;
       a.qa = qp + (size_t)b * n_utts;
-      a.out_f32 = last ? m->logits.as<float>() : m->act_f32[0].as<float>();
+      a.out_f32 = last ? w->logits.as<float>() : w->act_f32[0].as<float>();
       a.ld_out = last ? ldp : RoundUp(a.N, 4);
       a.n_store = a.N;
       if (!last) {
@@ -345,26 +362,26 @@ int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_o
         m->kept_valid = true;
       }
     } else if (m->kind == kKindBF16) {
-      ops.a[0] = m->act_bf16[b & 1].ptr;
+      ops.a[0] = w->act_bf16[b & 1].ptr;
       if (last) {
-        a.out_f32 = m->logits.as<float>();
+        a.out_f32 = w->logits.as<float>();
         a.ld_out = ldp;
         a.n_store = a.N;
       } else {
-        a.out_bf16 = m->act_bf16[(b + 1) & 1].as<__nv_bfloat16>();
+        a.out_bf16 = w->act_bf16[(b + 1) & 1].as<__nv_bfloat16>();
         a.ld_out = next_c;
         a.n_store = next_c;
       }
     } else {
-      ops.a[0] = m->act_f32[b & 1].ptr;
-      ops.a[1] = m->n_pass == 3 ? m->act_lo[b & 1].ptr : nullptr;
+      ops.a[0] = w->act_f32[b & 1].ptr;
+      ops.a[1] = m->n_pass == 3 ? w->act_lo[b & 1].ptr : nullptr;
       if (last) {
-        a.out_f32 = m->logits.as<float>();
+        a.out_f32 = w->logits.as<float>();
         a.ld_out = ldp;
         a.n_store = a.N;
       } else {
-        a.out_f32 = m->act_f32[(b + 1) & 1].as<float>();
-        a.out_lo = m->n_pass == 3 ? m->act_lo[(b + 1) & 1].as<float>() : nullptr;
+        a.out_f32 = w->act_f32[(b + 1) & 1].as<float>();
+        a.out_lo = m->n_pass == 3 ? w->act_lo[(b + 1) & 1].as<float>() : nullptr;
         a.round_tf32 = 1;
         a.ld_out = next_c;
         a.n_store = next_c;
@@ -375,13 +392,13 @@ int ForwardChunk(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_o
     if (m->kind == kKindI8 && !last) {
       QParam *q_next = qp + (size_t)(b + 1) * n_utts;
       CE_CHECK(QParamsLaunch(mm + 2 * (size_t)(b + 1) * n_utts, q_next, n_utts, s));
-      CE_CHECK(QuantizeLaunch(m->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile, q_next,
-                              m->act_u8.as<uint8_t>(), m->rowsum.as<int32_t>(), s));
+      CE_CHECK(QuantizeLaunch(w->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile, q_next,
+                              w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
     }
   }
 
-  CE_CHECK(FinalizeLaunch(m->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
-                          m->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
+  CE_CHECK(FinalizeLaunch(w->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
+                          w->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
                           m->log_prior.as<float>(), loglik_dev, NP, argmax_dev, s));
   return CE_GPU_OK;
 }
@@ -397,7 +414,10 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
   const int L = m->left, R = m->right, NP = m->prog.num_pdfs;
   const bool ll_host = loglik && !IsDevicePtr(loglik);
   const bool am_host = argmax && !IsDevicePtr(argmax);
-  int u0 = 0;
+  const bool overlap = m->overlap && m->keep_acc < 0;
+  if (overlap) CE_CUDA(cudaEventRecord(m->inputs_ready, s));
+  bool used[2] = {false, false};
+  int u0 = 0, chunk = 0;
   while (u0 < n_utts) {
     int u1 = u0;
     int64_t rows = 0;
@@ -408,29 +428,43 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
       rows += r;
       ++u1;
     }
+    ce_gpu_model::ChunkWs *w = &m->ws[overlap ? (chunk & 1) : 0];
+    cudaStream_t cs = overlap ? w->stream : s;
+    if (overlap && !used[chunk & 1]) {
+      CE_CUDA(cudaStreamWaitEvent(cs, m->inputs_ready, 0));
+      used[chunk & 1] = true;
+    }
     const int64_t f0 = frame_off[u0], nf = frame_off[u1] - f0;
     float *ll_dev = loglik;
     int32_t *am_dev = argmax;
     if (ll_host) {
-      CE_CHECK(m->stage_loglik.Reserve(sizeof(float) * (size_t)nf * NP));
-      ll_dev = m->stage_loglik.as<float>() - f0 * NP;     // row f0 lands on the staging buffer's row 0
+      CE_CHECK(w->stage_loglik.Reserve(sizeof(float) * (size_t)nf * NP));
+      ll_dev = w->stage_loglik.as<float>() - f0 * NP;     // row f0 lands on the staging buffer's row 0
     }
     if (am_host) {
-      CE_CHECK(m->stage_argmax.Reserve(sizeof(int32_t) * (size_t)nf));
-      am_dev = m->stage_argmax.as<int32_t>() - f0;
+      CE_CHECK(w->stage_argmax.Reserve(sizeof(int32_t) * (size_t)nf));
+      am_dev = w->stage_argmax.as<int32_t>() - f0;
     }
-    CE_CHECK(ForwardChunk(m, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, s));
+    CE_CHECK(ForwardChunk(m, w, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs));
     if (ll_host && nf > 0) {
-      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, m->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
-                              cudaMemcpyDeviceToHost, s));
+      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, w->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
+                              cudaMemcpyDeviceToHost, cs));
     }
     if (am_host && nf > 0) {
-      CE_CUDA(cudaMemcpyAsync(argmax + f0, m->stage_argmax.ptr, sizeof(int32_t) * (size_t)nf,
-                              cudaMemcpyDeviceToHost, s));
+      CE_CUDA(cudaMemcpyAsync(argmax + f0, w->stage_argmax.ptr, sizeof(int32_t) * (size_t)nf,
+                              cudaMemcpyDeviceToHost, cs));
     }
-    if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));
     u0 = u1;
+    ++chunk;
   }
+  if (overlap) {
+    for (int i = 0; i < 2; ++i) {
+      if (!used[i]) continue;
+      CE_CUDA(cudaEventRecord(m->ws[i].done, m->ws[i].stream));
+      CE_CUDA(cudaStreamWaitEvent(s, m->ws[i].done, 0));
+    }
+  }
+  if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));   // host outputs are complete on return
   return CE_GPU_OK;
 }
 

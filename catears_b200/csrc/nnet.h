@@ -40,13 +40,26 @@ struct ce_gpu_model {
   int64_t max_chunk_rows = 65536;
 
   // ---- workspace (one forward call at a time per handle) ----
-  ce::DevBuf stage_pcm, stage_feats, stage_loglik, stage_argmax;
+  ce::DevBuf stage_pcm, stage_feats;
   ce::DevBuf feats;                    // fbank output / staged features [frames x feat_dim]
-  ce::DevBuf x0;                       // padded fp32 input [M x feat_dim]
-  ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits, acc_dump;
-  ce::DevBuf minmax, qparams;
-  ce::Table fbank_chunks, cmvn_utts, utt_table, tile_table, outrow_table;
-  cudaStream_t own_stream = nullptr;
+  ce::Table fbank_chunks;
+  // Chunks of utterances alternate between two workspaces on two internal streams, so that the
+  // memory-bound kernels of one chunk (CMVN, quantise, log-softmax) overlap the tensor-core
+  // GEMMs of the other.
+  struct ChunkWs {
+    ce::DevBuf x0;                     // padded fp32 input [M x feat_dim]
+    ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits;
+    ce::DevBuf minmax, qparams;
+    ce::DevBuf stage_loglik, stage_argmax;
+    ce::Table cmvn_utts, utt_table, tile_table, outrow_table;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void Free();
+  };
+  ChunkWs ws[2];
+  cudaEvent_t inputs_ready = nullptr;
+  bool overlap = true;                 // CE_GPU_OVERLAP=0 runs every chunk on the caller's stream
+  ce::DevBuf acc_dump;
 
   // ---- debug: kept accumulators ----
   int keep_acc = -1;

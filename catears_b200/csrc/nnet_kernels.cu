@@ -201,6 +201,87 @@ finalize_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
   if (argmax && lane == 0) argmax[orow] = best_i == 0x7fffffff ? 0 : best_i;
 }
 
+// Same, for N % 4 == 0 and N <= 128 * NV: the row stays in registers (NV float4 per lane), so the
+// logits are read from HBM exactly once: 4N bytes in + 4N bytes out per frame.
+template <int NV>
+__global__ void __launch_bounds__(128)
+finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
+                         const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
+                         const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
+                         const float *__restrict__ log_prior, float *__restrict__ loglik,
+                         int64_t ld_out, int32_t *__restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int utt = tile_utt[row / kTileM];
+  const UttRows ur = utts[utt];
+  const int pos = row - ur.row_off;
+  if (pos < left || pos >= ur.rows - right) return;
+  const int64_t orow = out_row_off[utt] + (pos - left);
+  const float4 *x4 = reinterpret_cast<const float4 *>(logits + (int64_t)row * ld);
+  const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
+  const int n4 = N >> 2;
+
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < n4) ? __ldcs(x4 + c) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  }
+  float lse = 0.0f;
+  if (log_softmax) {
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) m = fmaxf(fmaxf(fmaxf(m, v[i].x), fmaxf(v[i].y, v[i].z)), v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < n4) s += (expf(v[i].x - m) + expf(v[i].y - m)) + (expf(v[i].z - m) + expf(v[i].w - m));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    lse = m + logf(s);
+  }
+  float best = -FLT_MAX;
+  int best_i = 0x7fffffff;
+  float4 *y4 = loglik ? reinterpret_cast<float4 *>(loglik + orow * ld_out) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < n4) {
+      const float4 lp = __ldg(lp4 + c);
+      float4 r = v[i];
+      if (log_softmax) {                                 // x -= log(sum)            vector.cc:120
+        r.x = __fsub_rn(r.x, lse); r.y = __fsub_rn(r.y, lse);
+        r.z = __fsub_rn(r.z, lse); r.w = __fsub_rn(r.w, lse);
+      }
+      r.x = __fsub_rn(r.x, lp.x); r.y = __fsub_rn(r.y, lp.y);   // AddVec(-1, log_prior_)  am.cc:111
+      r.z = __fsub_rn(r.z, lp.z); r.w = __fsub_rn(r.w, lp.w);
+      if (y4) __stcs(y4 + c, r);
+      const float e[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (e[q] > best) {                               // first maximum wins (columns ascend per lane)
+          best = e[q];
+          best_i = 4 * c + q;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if (argmax && lane == 0) argmax[orow] = best_i == 0x7fffffff ? 0 : best_i;
+}
+
 // Copies the valid rows [lo, P - hi) of one utterance out of a padded int32 matrix.
 }  // namespace
 
@@ -259,9 +340,28 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
                    int32_t *argmax, cudaStream_t s) {
   if (M <= 0) return CE_GPU_OK;
   ProfScope prof(kProfFinalize, s);
-  finalize_kernel<<<(M + 7) / 8, 256, 0, s>>>(logits, ld, N, M, tile_utt, utts, out_row_off, left,
-                                             right, log_softmax ? 1 : 0, log_prior, loglik, ld_out,
-                                             argmax);
+  const bool vec = (N % 4 == 0) && (ld % 4 == 0) && (ld_out % 4 == 0) && N <= 4096 &&
+                   ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(loglik) |
+                     reinterpret_cast<uintptr_t>(log_prior)) & 15) == 0;
+#define CE_FINALIZE(NV)                                                                            \
+  finalize_rowcache_kernel<NV><<<(M + 3) / 4, 128, 0, s>>>(logits, ld, N, M, tile_utt, utts,       \
+                                                           out_row_off, left, right,               \
+                                                           log_softmax ? 1 : 0, log_prior, loglik, \
+                                                           ld_out, argmax)
+  if (vec && N <= 1024) {
+    CE_FINALIZE(8);
+  } else if (vec && N <= 2048) {
+    CE_FINALIZE(16);
+  } else if (vec && N <= 3072) {
+    CE_FINALIZE(24);
+  } else if (vec) {
+    CE_FINALIZE(32);
+  } else {
+    finalize_kernel<<<(M + 7) / 8, 256, 0, s>>>(logits, ld, N, M, tile_utt, utts, out_row_off, left,
+                                               right, log_softmax ? 1 : 0, log_prior, loglik, ld_out,
+                                               argmax);
+  }
+#undef CE_FINALIZE
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
