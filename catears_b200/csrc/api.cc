@@ -318,16 +318,13 @@ int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sam
   }
   CE_CHECK(UseDevice(m->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int F = m->prog.feat_dim;
   const int64_t base = utt_sample_offsets[0], total_samples = utt_sample_offsets[n_utts];
   const void *pcm_dev = nullptr;
   CE_CHECK(StageIn(pcm + base, sizeof(int16_t) * (size_t)(total_samples - base), &m->stage_pcm, s, &pcm_dev));
   std::vector<int64_t> soff(n_utts + 1);
   for (int u = 0; u <= n_utts; ++u) soff[u] = utt_sample_offsets[u] - base;
-  CE_CHECK(m->feats.Reserve(sizeof(float) * (size_t)total_frames * F));
-  CE_CHECK(FbankLaunch(static_cast<const int16_t *>(pcm_dev), total_samples - base, soff.data(),
-                       foff.data(), n_utts, F, m->feats.as<float>(), F, &m->fbank_chunks, s));
-  return NnetForward(m, m->feats.as<float>(), foff.data(), n_utts, m->has_cmvn, loglik, argmax, s);
+  return PcmForward(m, static_cast<const int16_t *>(pcm_dev), total_samples - base, soff.data(),
+                    foff.data(), n_utts, loglik, argmax, s);
 }
 
 int ce_gpu_nnet_keep_acc(ce_gpu_model_t *m, int linear_ordinal) {

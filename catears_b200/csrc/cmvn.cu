@@ -39,7 +39,7 @@ struct CmvnStep {    // frame-index-only part of the chain (t < 600; t >= 599 us
 constexpr int kUnroll = 16;
 
 // One thread per (utt, d), flattened so that warps stay full for any mel.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
             int mel, int pad_left, int pad_right, float *__restrict__ out, int64_t out_stride) {
@@ -165,9 +165,9 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
   }
   CE_CHECK(utts->Upload(bytes, s));
   const int64_t n_threads = (int64_t)n_utts * num_mel;
-  const unsigned grid = (unsigned)((n_threads + 255) / 256);
+  const unsigned grid = (unsigned)((n_threads + 127) / 128);
   ProfScope prof(kProfCmvn, s);
-  cmvn_kernel<<<grid, 256, 0, s>>>(global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(),
+  cmvn_kernel<<<grid, 128, 0, s>>>(global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(),
                                      n_utts, num_mel, pad_left, pad_right, out_dev, out_stride);
   CE_LAUNCHED();
   return CE_GPU_OK;

@@ -255,7 +255,7 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
 // kernel
 // ---------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(128)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
             const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,

@@ -16,7 +16,7 @@
 #include <algorithm>
 
 void ce_gpu_model::ChunkWs::Free() {
-  x0.Free();
+  x0.Free(); feats.Free(); fbank_chunks.Free();
   for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
   act_u8.Free(); rowsum.Free(); logits.Free(); minmax.Free(); qparams.Free();
   stage_loglik.Free(); stage_argmax.Free();
@@ -208,9 +208,15 @@ RowUse MakeRowUse(const ce_gpu_model *m, int producer /* -1 = network input */) 
 
 // Output rows are addressed by absolute frame index (frame_off), so loglik_dev / argmax_dev are
 // the bases of the whole batch's outputs.
-int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const float *feats_dev,
-                 const int64_t *frame_off, int n_utts, bool apply_cmvn, float *loglik_dev,
-                 int32_t *argmax_dev, cudaStream_t s) {
+struct PcmSource {
+  const int16_t *pcm_dev = nullptr;     // nullptr: features are given
+  int64_t total_samples = 0;
+  const int64_t *sample_off = nullptr;  // [n_utts + 1] of this chunk
+};
+
+int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
+                 const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
+                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
   const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
   const int nb = (int)m->blocks.size();
 
@@ -270,9 +276,22 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const float *feats_d
     }
   }
 
+  // ---- fbank of this chunk's utterances (when the input is PCM) ----
+  std::vector<int64_t> local_off;
+  const int64_t *feat_off = frame_off;
+  if (src.pcm_dev) {
+    local_off.resize(n_utts + 1);
+    for (int u = 0; u <= n_utts; ++u) local_off[u] = frame_off[u] - frame_off[0];
+    CE_CHECK(w->feats.Reserve(sizeof(float) * (size_t)local_off[n_utts] * F));
+    CE_CHECK(FbankLaunch(src.pcm_dev, src.total_samples, src.sample_off, local_off.data(), n_utts, F,
+                         w->feats.as<float>(), F, &w->fbank_chunks, s));
+    feats_dev = w->feats.as<float>();
+    feat_off = local_off.data();
+  }
+
   // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155 ----
   CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
-                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, frame_off, row_off64.data(),
+                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, feat_off, row_off64.data(),
                       n_utts, F, L, R, w->x0.as<float>(), F, &w->cmvn_utts, s));
 
   // ---- network input in the operand format of the data path ----
@@ -405,8 +424,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const float *feats_d
 
 }  // namespace
 
-int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
-                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
+namespace {
+int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
+               int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
   if (apply_cmvn && !m->has_cmvn) {
     SetError("the model was loaded without CMVN statistics");
     return CE_GPU_EINVAL;
@@ -445,7 +465,9 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
       CE_CHECK(w->stage_argmax.Reserve(sizeof(int32_t) * (size_t)nf));
       am_dev = w->stage_argmax.as<int32_t>() - f0;
     }
-    CE_CHECK(ForwardChunk(m, w, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs));
+    PcmSource src = all;
+    if (all.pcm_dev) src.sample_off = all.sample_off + u0;
+    CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs));
     if (ll_host && nf > 0) {
       CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, w->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
                               cudaMemcpyDeviceToHost, cs));
@@ -466,6 +488,22 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
   }
   if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));   // host outputs are complete on return
   return CE_GPU_OK;
+}
+}  // namespace
+
+int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
+                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
+  return ForwardAll(m, PcmSource(), feats_dev, frame_off, n_utts, apply_cmvn, loglik, argmax, s);
+}
+
+int PcmForward(ce_gpu_model *m, const int16_t *pcm_dev, int64_t total_samples,
+               const int64_t *sample_off, const int64_t *frame_off, int n_utts, float *loglik,
+               int32_t *argmax, cudaStream_t s) {
+  PcmSource src;
+  src.pcm_dev = pcm_dev;
+  src.total_samples = total_samples;
+  src.sample_off = sample_off;
+  return ForwardAll(m, src, nullptr, frame_off, n_utts, m->has_cmvn, loglik, argmax, s);
 }
 
 }  // namespace ce

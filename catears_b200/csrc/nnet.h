@@ -47,6 +47,8 @@ struct ce_gpu_model {
   // memory-bound kernels of one chunk (CMVN, quantise, log-softmax) overlap the tensor-core
   // GEMMs of the other.
   struct ChunkWs {
+    ce::DevBuf feats;                  // this chunk's fbank output [frames x feat_dim]
+    ce::Table fbank_chunks;
     ce::DevBuf x0;                     // padded fp32 input [M x feat_dim]
     ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits;
     ce::DevBuf minmax, qparams;
@@ -85,6 +87,12 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
 // are copied back chunk by chunk and are complete on return).
 int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
                 bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s);
+
+// The whole path from PCM: like NnetForward, but every chunk first runs the fbank kernel on its
+// own utterances (pcm_dev / sample_off as in ce_gpu_fbank), on the chunk's stream.
+int PcmForward(ce_gpu_model *m, const int16_t *pcm_dev, int64_t total_samples,
+               const int64_t *sample_off, const int64_t *frame_off, int n_utts, float *loglik,
+               int32_t *argmax, cudaStream_t s);
 
 }  // namespace ce
 #endif  // CE_GPU_NNET_H_

@@ -84,8 +84,8 @@ __device__ __forceinline__ uint32_t QuantOne(float v, float scale, float zp) {
 }
 
 // One warp per row: x [M x ld_in] fp32 (C columns) -> q [M x c_pad] u8 (zero padded) and
-// rowsum[row] = sum of the C codes.
-__global__ void __launch_bounds__(256)
+// rowsum[row] = sum of the C codes.  Four 16-byte loads per lane are in flight at a time.
+__global__ void __launch_bounds__(128)
 quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_pad,
                 const int32_t *__restrict__ tile_utt, const QParam *__restrict__ qp,
                 uint8_t *__restrict__ q, int32_t *__restrict__ rowsum) {
@@ -99,20 +99,32 @@ quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_
   uint32_t *o = reinterpret_cast<uint32_t *>(q + (int64_t)row * c_pad);
   int32_t sum = 0;
   const bool vec = ((ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  for (int c4 = lane * 4; c4 < c_pad; c4 += 128) {
-    uint32_t code[4] = {0, 0, 0, 0};
-    if (vec && c4 + 4 <= C) {
-      const float4 f = *reinterpret_cast<const float4 *>(r + c4);
-      code[0] = QuantOne(f.x, p.scale, zp);
-      code[1] = QuantOne(f.y, p.scale, zp);
-      code[2] = QuantOne(f.z, p.scale, zp);
-      code[3] = QuantOne(f.w, p.scale, zp);
-    } else {
-      for (int j = 0; j < 4; ++j)
-        if (c4 + j < C) code[j] = QuantOne(r[c4 + j], p.scale, zp);
+  for (int base = 0; base < c_pad; base += 512) {
+    float4 f[4];
+    bool full[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c4 = base + u * 128 + lane * 4;
+      full[u] = vec && c4 + 4 <= C;
+      f[u] = full[u] ? __ldcs(reinterpret_cast<const float4 *>(r + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    sum += (int32_t)(code[0] + code[1] + code[2] + code[3]);
-    o[c4 >> 2] = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c4 = base + u * 128 + lane * 4;
+      if (c4 >= c_pad) continue;
+      uint32_t code[4] = {0, 0, 0, 0};
+      if (full[u]) {
+        code[0] = QuantOne(f[u].x, p.scale, zp);
+        code[1] = QuantOne(f[u].y, p.scale, zp);
+        code[2] = QuantOne(f[u].z, p.scale, zp);
+        code[3] = QuantOne(f[u].w, p.scale, zp);
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (c4 + j < C) code[j] = QuantOne(r[c4 + j], p.scale, zp);
+      }
+      sum += (int32_t)(code[0] + code[1] + code[2] + code[3]);
+      o[c4 >> 2] = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+    }
   }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
@@ -318,7 +330,7 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
     return CE_GPU_EINVAL;
   }
   ProfScope prof(kProfQuantize, s);
-  quantize_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
+  quantize_kernel<<<(M + 3) / 4, 128, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
