@@ -120,6 +120,18 @@ int UseDevice(int device) {
   return CE_GPU_OK;
 }
 
+int SmCount() {
+  static thread_local int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 bool IsDevicePtr(const void *p) {
   if (p == nullptr) return false;
   cudaPointerAttributes attr;

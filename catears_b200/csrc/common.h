@@ -66,6 +66,9 @@ int ProfRead(double *ms, int64_t *launches);
 // Makes `device` current; fails with CE_GPU_ENODEVICE when there is none / not sm_100.
 int UseDevice(int device);
 
+// Multiprocessor count of the current device (cached).
+int SmCount();
+
 // true if `p` is device memory (cudaMalloc / torch), false for host memory.
 bool IsDevicePtr(const void *p);
 

@@ -11,6 +11,8 @@
 
 #include <float.h>
 
+#include <algorithm>
+
 namespace ce {
 namespace {
 
@@ -38,15 +40,15 @@ minmax_kernel(const float *__restrict__ x, int64_t ld, int C, int M,
               const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts, RowUse use,
               uint32_t *__restrict__ minmax) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
   const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
   int pos = row, P = M;
   if (utts) {
     pos = row - utts[utt].row_off;
     P = utts[utt].rows;
   }
-  if (!RowUsed(pos, P, use)) return;
+  if (!RowUsed(pos, P, use)) continue;
   float vmin = FLT_MAX, vmax = -FLT_MAX;
   const float *r = x + (int64_t)row * ld;
   for (int c = lane; c < C; c += 32) {
@@ -62,6 +64,7 @@ minmax_kernel(const float *__restrict__ x, int64_t ld, int C, int M,
   if (lane == 0 && vmin <= vmax) {
     atomicMin(minmax + 2 * utt, OrderedFromFloat(vmin));
     atomicMax(minmax + 2 * utt + 1, OrderedFromFloat(vmax));
+  }
   }
 }
 
@@ -85,13 +88,13 @@ __device__ __forceinline__ uint32_t QuantOne(float v, float scale, float zp) {
 
 // One warp per row: x [M x ld_in] fp32 (C columns) -> q [M x c_pad] u8 (zero padded) and
 // rowsum[row] = sum of the C codes.  Four 16-byte loads per lane are in flight at a time.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_pad,
                 const int32_t *__restrict__ tile_utt, const QParam *__restrict__ qp,
                 uint8_t *__restrict__ q, int32_t *__restrict__ rowsum) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
   const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
   const QParam p = qp[utt];
   const float zp = (float)p.zero_point;
@@ -129,6 +132,7 @@ quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
   if (lane == 0 && rowsum) rowsum[row] = sum;
+  }
 }
 
 __device__ __forceinline__ float RoundTf32(float v) {
@@ -216,19 +220,19 @@ finalize_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
 // Same, for N % 4 == 0 and N <= 128 * NV: the row stays in registers (NV float4 per lane), so the
 // logits are read from HBM exactly once: 4N bytes in + 4N bytes out per frame.
 template <int NV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
                          const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
                          const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
                          const float *__restrict__ log_prior, float *__restrict__ loglik,
                          int64_t ld_out, int32_t *__restrict__ argmax) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
   const int utt = tile_utt[row / kTileM];
   const UttRows ur = utts[utt];
   const int pos = row - ur.row_off;
-  if (pos < left || pos >= ur.rows - right) return;
+  if (pos < left || pos >= ur.rows - right) continue;
   const int64_t orow = out_row_off[utt] + (pos - left);
   const float4 *x4 = reinterpret_cast<const float4 *>(logits + (int64_t)row * ld);
   const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
@@ -292,6 +296,7 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
     }
   }
   if (argmax && lane == 0) argmax[orow] = best_i == 0x7fffffff ? 0 : best_i;
+  }
 }
 
 // Copies the valid rows [lo, P - hi) of one utterance out of a padded int32 matrix.
@@ -309,7 +314,7 @@ int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_u
                  const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s) {
   if (M <= 0) return CE_GPU_OK;
   ProfScope prof(kProfQuantize, s);
-  minmax_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, ld, C, M, tile_utt, utts, use, minmax);
+  minmax_kernel<<<std::min((M + 7) / 8, 4 * SmCount()), 256, 0, s>>>(x, ld, C, M, tile_utt, utts, use, minmax);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
@@ -330,7 +335,9 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
     return CE_GPU_EINVAL;
   }
   ProfScope prof(kProfQuantize, s);
-  quantize_kernel<<<(M + 3) / 4, 128, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
+  // Bounded grid (2 blocks per SM): leaves room for a GEMM CTA of the other chunk on every SM.
+  const unsigned grid = (unsigned)std::min((M + 7) / 8, 2 * SmCount());
+  quantize_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
@@ -355,8 +362,11 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
   const bool vec = (N % 4 == 0) && (ld % 4 == 0) && (ld_out % 4 == 0) && N <= 4096 &&
                    ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(loglik) |
                      reinterpret_cast<uintptr_t>(log_prior)) & 15) == 0;
+  // Bounded grid: one 4-row block per SM (a row of 3072 logits lives in 96 registers per lane),
+  // which still leaves the registers a GEMM CTA of the other chunk needs.
+  const unsigned fgrid = (unsigned)std::min((M + 3) / 4, SmCount());
 #define CE_FINALIZE(NV)                                                                            \
-  finalize_rowcache_kernel<NV><<<(M + 3) / 4, 128, 0, s>>>(logits, ld, N, M, tile_utt, utts,       \
+  finalize_rowcache_kernel<NV><<<fgrid, 128, 0, s>>>(logits, ld, N, M, tile_utt, utts,             \
                                                            out_row_off, left, right,               \
                                                            log_softmax ? 1 : 0, log_prior, loglik, \
                                                            ld_out, argmax)
