@@ -22,9 +22,12 @@ void ce_gpu_model::ChunkWs::Free() {
   stage_loglik.Free(); stage_argmax.Free();
   cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
   if (stream) cudaStreamDestroy(stream);
+  if (stream_hi) cudaStreamDestroy(stream_hi);
   if (done) cudaEventDestroy(done);
-  stream = nullptr;
-  done = nullptr;
+  if (to_hi) cudaEventDestroy(to_hi);
+  if (to_lo) cudaEventDestroy(to_lo);
+  stream = stream_hi = nullptr;
+  done = to_hi = to_lo = nullptr;
 }
 
 ce_gpu_model::~ce_gpu_model() {
@@ -181,9 +184,14 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     if (v >= kTileM) m->max_chunk_rows = v;
   }
   if (const char *e = getenv("CE_GPU_OVERLAP")) m->overlap = atoi(e) != 0;
+  int prio_lo = 0, prio_hi = 0;
+  CE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < 2; ++i) {
-    CE_CUDA(cudaStreamCreateWithFlags(&m->ws[i].stream, cudaStreamNonBlocking));
+    CE_CUDA(cudaStreamCreateWithPriority(&m->ws[i].stream, cudaStreamNonBlocking, prio_lo));
+    CE_CUDA(cudaStreamCreateWithPriority(&m->ws[i].stream_hi, cudaStreamNonBlocking, prio_hi));
     CE_CUDA(cudaEventCreateWithFlags(&m->ws[i].done, cudaEventDisableTiming));
+    CE_CUDA(cudaEventCreateWithFlags(&m->ws[i].to_hi, cudaEventDisableTiming));
+    CE_CUDA(cudaEventCreateWithFlags(&m->ws[i].to_lo, cudaEventDisableTiming));
   }
   CE_CUDA(cudaEventCreateWithFlags(&m->inputs_ready, cudaEventDisableTiming));
   return CE_GPU_OK;
@@ -214,9 +222,11 @@ struct PcmSource {
   const int64_t *sample_off = nullptr;  // [n_utts + 1] of this chunk
 };
 
+// s: stream of the memory-bound kernels; s_gemm: stream of the GEMMs (== s when chunks are not
+// overlapped).
 int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
                  const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
-                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
+                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s, cudaStream_t s_gemm) {
   const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
   const int nb = (int)m->blocks.size();
 
@@ -406,7 +416,15 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         a.n_store = next_c;
       }
     }
-    CE_CHECK(GemmLaunch(m->kind, ops, a, s));
+    if (s_gemm != s) {
+      CE_CUDA(cudaEventRecord(w->to_hi, s));
+      CE_CUDA(cudaStreamWaitEvent(s_gemm, w->to_hi, 0));
+    }
+    CE_CHECK(GemmLaunch(m->kind, ops, a, s_gemm));
+    if (s_gemm != s && (m->kind == kKindI8 || last)) {   // float paths chain GEMM -> GEMM
+      CE_CUDA(cudaEventRecord(w->to_lo, s_gemm));
+      CE_CUDA(cudaStreamWaitEvent(s, w->to_lo, 0));
+    }
 
     if (m->kind == kKindI8 && !last) {
       QParam *q_next = qp + (size_t)(b + 1) * n_utts;
@@ -467,7 +485,8 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     }
     PcmSource src = all;
     if (all.pcm_dev) src.sample_off = all.sample_off + u0;
-    CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs));
+    CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
+                          overlap ? w->stream_hi : cs));
     if (ll_host && nf > 0) {
       CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, w->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
                               cudaMemcpyDeviceToHost, cs));

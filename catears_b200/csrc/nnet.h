@@ -54,8 +54,11 @@ struct ce_gpu_model {
     ce::DevBuf minmax, qparams;
     ce::DevBuf stage_loglik, stage_argmax;
     ce::Table cmvn_utts, utt_table, tile_table, outrow_table;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
+    // `stream` (low priority) carries the memory-bound kernels, `stream_hi` (high priority) the
+    // GEMMs: whenever a GEMM is ready its CTAs are placed first and the other chunk's
+    // quantise / log-softmax blocks fill the registers and threads it leaves free.
+    cudaStream_t stream = nullptr, stream_hi = nullptr;
+    cudaEvent_t done = nullptr, to_hi = nullptr, to_lo = nullptr;
     void Free();
   };
   ChunkWs ws[2];

@@ -335,8 +335,7 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
     return CE_GPU_EINVAL;
   }
   ProfScope prof(kProfQuantize, s);
-  // Bounded grid (2 blocks per SM): leaves room for a GEMM CTA of the other chunk on every SM.
-  const unsigned grid = (unsigned)std::min((M + 7) / 8, 2 * SmCount());
+  const unsigned grid = (unsigned)std::min((M + 7) / 8, 32 * SmCount());
   quantize_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
   CE_LAUNCHED();
   return CE_GPU_OK;
@@ -362,9 +361,7 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
   const bool vec = (N % 4 == 0) && (ld % 4 == 0) && (ld_out % 4 == 0) && N <= 4096 &&
                    ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(loglik) |
                      reinterpret_cast<uintptr_t>(log_prior)) & 15) == 0;
-  // Bounded grid: one 4-row block per SM (a row of 3072 logits lives in 96 registers per lane),
-  // which still leaves the registers a GEMM CTA of the other chunk needs.
-  const unsigned fgrid = (unsigned)std::min((M + 3) / 4, SmCount());
+  const unsigned fgrid = (unsigned)std::min((M + 3) / 4, 32 * SmCount());
 #define CE_FINALIZE(NV)                                                                            \
   finalize_rowcache_kernel<NV><<<fgrid, 128, 0, s>>>(logits, ld, N, M, tile_utt, utts,             \
                                                            out_row_off, left, right,               \
