@@ -313,7 +313,13 @@ def run_gpu(args):
     sampler.start()
     time.sleep(0.3)
     api.launch_count(reset=True)
+    if os.environ.get("BENCH_PROFILE_OVERLAP"):
+        api.profile_enable(True)
     ms = timed(step_device, args.steps)
+    if os.environ.get("BENCH_PROFILE_OVERLAP"):
+        sys.stderr.write("overlapped per-kernel ms/step: %s\n" % {k: round(v[0] / args.steps, 3)
+                                                                 for k, v in api.profile_read().items()})
+        api.profile_enable(False)
     launches = api.launch_count()
     clocks = sampler.stop()
     value = audio_per_step * args.steps / (ms * 1e-3)
