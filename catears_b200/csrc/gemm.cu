@@ -32,22 +32,33 @@
 namespace ce {
 namespace {
 
-constexpr int kStages = 3;
-constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB
-constexpr int kBBytes = kTileN * kTileKBytes;            // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB: 128 rows of A per CTA per stage
 constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quadrant (column halves)
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
 constexpr int kParamBytes = 4 * kTileN * 4;              // bias, bn scale, bn offset, int correction
-constexpr int kOffStage = kStages * kStageBytes;         // output staging (1024-aligned)
-constexpr int kOffParams = kOffStage + kEpiWarps * kOutTileBytes;
-constexpr int kOffBars = kOffParams + kParamBytes;
-constexpr int kSmemBytes = 1024 /*alignment slack*/ + kOffBars + 256;
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// CG = 1: one CTA computes a 128 x 256 tile.  CG = 2 (cta_group::2): a pair of CTAs on one TPC
+// computes a 256 x 256 tile with one tcgen05.mma M=256 -- each CTA stages its own 128 rows of A
+// and HALF of the B tile (128 of the 256 weight rows), so per CTA the L2 -> smem traffic and the
+// shared-memory operand reads of the tensor core drop by a third, and the smaller stages leave
+// room for a deeper ring.
+template <int CG>
+struct Cfg {
+  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  static constexpr int kBRows = kTileN / CG;             // weight rows staged per CTA
+  static constexpr int kBBytes = kBRows * kTileKBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOffStage = kStages * kStageBytes;   // output staging (1024-aligned)
+  static constexpr int kOffParams = kOffStage + kEpiWarps * kOutTileBytes;
+  static constexpr int kOffBars = kOffParams + kParamBytes;
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kOffBars + 256;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(2 * kStages + 2 * kAccStages + 1 <= 32, "barrier block");
+};
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -116,6 +127,44 @@ __device__ __forceinline__ void epi_bar() {               // the 256 epilogue th
   asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
+// ---- cluster (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank`.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data lands in THIS CTA's smem, the bytes are counted on the leader's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// tcgen05.commit of the pair: arrives on the barrier at this smem offset in BOTH CTAs.
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :
+      : "r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -127,30 +176,24 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
                : "memory");
 }
 
-template <int KIND>
+#define CE_TC_MMA(GROUP, KINDSTR)                                                          \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                            \
+               "tcgen05.mma.cta_group::" GROUP ".kind::" KINDSTR " [%0], %1, %2, %3, p;\n\t}"  \
+               :                                                                          \
+               : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)       \
+               : "memory")
+
+template <int KIND, int CG>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                        uint32_t idesc, uint32_t accumulate) {
-  if (KIND == kKindI8) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else if (KIND == kKindBF16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+  if (CG == 1) {
+    if (KIND == kKindI8) CE_TC_MMA("1", "i8");
+    else if (KIND == kKindBF16) CE_TC_MMA("1", "f16");
+    else CE_TC_MMA("1", "tf32");
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (KIND == kKindI8) CE_TC_MMA("2", "i8");
+    else if (KIND == kKindBF16) CE_TC_MMA("2", "f16");
+    else CE_TC_MMA("2", "tf32");
   }
 }
 
@@ -182,12 +225,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int KIND>
+template <int KIND, int CG>
 __device__ __forceinline__ uint32_t make_idesc() {
   const uint32_t c_fmt = (KIND == kKindI8) ? 2u : 1u;                 // S32 : F32
   const uint32_t ab_fmt = (KIND == kKindI8) ? 0u : (KIND == kKindBF16) ? 1u : 2u;   // U8, BF16, TF32
   return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-         ((uint32_t)(kTileM >> 4) << 24);
+         ((uint32_t)((kTileM * CG) >> 4) << 24);                      // M = 128 (one CTA) / 256 (pair)
 }
 
 __device__ __forceinline__ float round_tf32(float v) {
@@ -254,21 +297,26 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
 // ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
-template <int KIND>
+template <int KIND, int CG>
 __global__ void __maxnreg__(128)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
             const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
             const GemmArgs p) {
+  using C = Cfg<CG>;
+  constexpr int kStages = C::kStages;
+  constexpr int kBBytes = C::kBBytes;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *smem_a = smem;                                   // [kStages][kABytes]
   unsigned char *smem_b = smem + kStages * kABytes;               // [kStages][kBBytes]
-  unsigned char *smem_out = smem + kOffStage;                     // [kEpiWarps][kOutTileBytes]
-  float *sp = reinterpret_cast<float *>(smem + kOffParams);       // [4][kTileN]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBars);
-  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  unsigned char *smem_out = smem + C::kOffStage;                  // [kEpiWarps][kOutTileBytes]
+  float *sp = reinterpret_cast<float *>(smem + C::kOffParams);    // [4][kTileN]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOffBars);
+  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot.
+  // With CG == 2 the same block exists in both CTAs; `full` and `tmem_empty` are used in the
+  // leader (cluster rank 0) only, `empty` and `tmem_full` in both (multicast commits).
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages);
@@ -277,6 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;      // position in the CTA pair
+  const bool leader = rank == 0;
+  const int group_id = blockIdx.x / CG;                          // tile-processing unit (CTA or pair)
+  const int n_groups = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -285,24 +337,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, kEpiWarps);
+      mbar_init(bar_tempty + 8 * i, kEpiWarps * CG);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                       // the peer's barriers exist before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_tiles = (p.M + kTileM - 1) / kTileM;
+  constexpr int kGroupM = kTileM * CG;                   // rows per tile of the processing unit
+  const int m_tiles = (p.M + kGroupM - 1) / kGroupM;
   const int n_tiles = (p.N + kTileN - 1) / kTileN;
   const int total_tiles = m_tiles * n_tiles;
   constexpr int kEltBytes = (KIND == kKindI8) ? 1 : (KIND == kKindBF16) ? 2 : 4;
@@ -312,13 +374,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int n_steps = p.n_pass * steps_per_pass;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own operand slices) ===============
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kTileM;
-        const int n0 = (tile % n_tiles) * kTileN;
+      const uint32_t full0 = (CG == 2) ? map_to_cta(bar_full, 0) : bar_full;   // leader's barriers
+      for (int tile = group_id; tile < total_tiles; tile += n_groups) {
+        const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;
+        const int n0 = (tile % n_tiles) * kTileN + (int)rank * C::kBRows;
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap *ma = p.pass_a[ps] ? &map_a1 : &map_a0;
           const CUtensorMap *mb = p.pass_b[ps] ? &map_b1 : &map_b0;
@@ -326,10 +389,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             const int row = m0 + p.tap_off[tap];
             for (int kb = 0; kb < kb_per_tap; ++kb) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-              tma_load_2d(smem_u32(smem_a + stage * kABytes), ma, bar_full + 8 * stage, kb * kTileK, row);
-              tma_load_2d(smem_u32(smem_b + stage * kBBytes), mb, bar_full + 8 * stage,
-                          tap * p.c_pad + kb * kTileK, n0);
+              if (p.debug & 4) {
+                if (leader) mbar_arrive(bar_full + 8 * stage);
+              } else if (CG == 1) {
+                mbar_expect_tx(bar_full + 8 * stage, C::kStageBytes);
+                tma_load_2d(smem_u32(smem_a + stage * kABytes), ma, bar_full + 8 * stage, kb * kTileK, row);
+                tma_load_2d(smem_u32(smem_b + stage * kBBytes), mb, bar_full + 8 * stage,
+                            tap * p.c_pad + kb * kTileK, n0);
+              } else {
+                if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * C::kStageBytes);   // both CTAs' bytes
+                tma_load_2d_pair(smem_u32(smem_a + stage * kABytes), ma, full0 + 8 * stage, kb * kTileK, row);
+                tma_load_2d_pair(smem_u32(smem_b + stage * kBBytes), mb, full0 + 8 * stage,
+                                 tap * p.c_pad + kb * kTileK, n0);
+              }
               if (++stage == kStages) {
                 stage = 0;
                 phase ^= 1;
@@ -340,14 +412,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc<KIND>();
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc<KIND, CG>();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = group_id; tile < total_tiles; tile += n_groups) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileN);
@@ -356,19 +428,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           tc_fence_after();
           const uint64_t da = make_desc(smem_u32(smem_a + stage * kABytes));
           const uint64_t db = make_desc(smem_u32(smem_b + stage * kBBytes));
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < kTileKBytes / 32; ++k) {
-            // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-            tc_mma<KIND>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (step | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kTileKBytes / 32; ++k) {
+              // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+              tc_mma<KIND, CG>(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                               (step | k) != 0 ? 1u : 0u);
+            }
           }
-          tc_commit(bar_empty + 8 * stage);              // frees the smem slot when the MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+          if (CG == 1) tc_commit(bar_empty + 8 * stage); else tc_commit_pair(bar_empty + 8 * stage);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(bar_tfull + 8 * acc);                  // accumulator complete
+        // accumulator complete (in both CTAs of a pair)
+        if (CG == 1) tc_commit(bar_tfull + 8 * acc); else tc_commit_pair(bar_tfull + 8 * acc);
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -386,14 +462,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int flags = (p.relu ? 1 : 0) | (p.bn_scale ? 2 : 0) | (p.minmax ? 4 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / n_tiles;
-      const int m0 = m_tile * kTileM;
+    const uint32_t tempty0 = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
+    const int row_tiles = (p.M + kTileM - 1) / kTileM;
+    for (int tile = group_id; tile < total_tiles; tile += n_groups) {
+      const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
       const int n0 = (tile % n_tiles) * kTileN;
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
 
       // ---- per-tile constants; per-column parameters -> shared memory ----
-      const int utt = p.tile_utt ? p.tile_utt[m_tile] : 0;
+      const int utt = p.tile_utt ? p.tile_utt[min(m0 / kTileM, row_tiles - 1)] : 0;
       int32_t zp_a = 0;
       RowConst rc;
       rc.row_corr = 0;
@@ -455,6 +532,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         if (col0 >= p.n_store) break;                    // warp-uniform
         uint32_t raw[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), raw);
+        if (p.debug & 1) continue;
         float v[32];
         float cmin = FLT_MAX, cmax = -FLT_MAX;           // this chunk's share of FindMinMax
         switch (flags) {
@@ -544,7 +622,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       // accumulator drained: hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(bar_tempty + 8 * acc); else mbar_arrive_cluster(tempty0 + 8 * acc);
+      }
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -571,10 +651,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                       // the peer is done with this CTA's smem / TMEM
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
-                 : "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                   : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                   : "memory");
+    }
   }
 }
 
@@ -659,8 +745,9 @@ int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t 
   return CE_GPU_OK;
 }
 
-template <int KIND>
+template <int KIND, int CG>
 int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
+  using C = Cfg<CG>;
   CUtensorMap ma0, ma1, mb0, mb1, mo0, mo1;
   const bool out_is_bf16 = (KIND == kKindBF16) && args.out_bf16 != nullptr;
   const void *o0 = out_is_bf16 ? static_cast<const void *>(args.out_bf16) : static_cast<const void *>(args.out_f32);
@@ -676,34 +763,47 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   }
   CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
   CE_CHECK(MakeMap(KIND, ops.a[1] ? ops.a[1] : ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma1));
-  CE_CHECK(MakeMap(KIND, ops.b[0], ops.rows_b, ops.k_total, kTileN, &mb0));
-  CE_CHECK(MakeMap(KIND, ops.b[1] ? ops.b[1] : ops.b[0], ops.rows_b, ops.k_total, kTileN, &mb1));
+  CE_CHECK(MakeMap(KIND, ops.b[0], ops.rows_b, ops.k_total, C::kBRows, &mb0));
+  CE_CHECK(MakeMap(KIND, ops.b[1] ? ops.b[1] : ops.b[0], ops.rows_b, ops.k_total, C::kBRows, &mb1));
   static thread_local bool configured[64] = {false};
   int dev = 0;
   CE_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !configured[dev]) {
-    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes));
     configured[dev] = true;
   }
-  static thread_local int sm_count[64] = {0};
-  if (dev < 64 && sm_count[dev] == 0) {
-    CE_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int m_tiles = (args.M + kTileM - 1) / kTileM;
+  const int group_m = kTileM * CG;
+  const int m_tiles = (args.M + group_m - 1) / group_m;
   const int n_tiles = (args.N + kTileN - 1) / kTileN;
   const int64_t tiles = (int64_t)m_tiles * n_tiles;
   if (tiles <= 0) return CE_GPU_OK;
-  const int sms = dev < 64 ? sm_count[dev] : 148;
-  const unsigned grid = (unsigned)std::min<int64_t>(tiles, sms);
+  const int groups = (int)std::min<int64_t>(tiles, SmCount() / CG);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   ProfScope prof(kProfGemm, s);
-  gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma0, ma1, mb0, mb1, mo0, mo1, args);
+  CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG>, ma0, ma1, mb0, mb1, mo0, mo1, args));
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
 
 }  // namespace
 
-int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
+int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaStream_t s) {
+  GemmArgs args = args_in;
+  static const int debug_bits = getenv("CE_GPU_GEMM_DEBUG") ? atoi(getenv("CE_GPU_GEMM_DEBUG")) : 0;
+  args.debug = debug_bits;
   if (args.c_pad <= 0 || args.c_pad % KindTileK(kind) != 0 || args.n_taps < 1 ||
       args.n_taps > kMaxTaps || args.n_pass < 1 || args.n_pass > 3) {
     SetError("GemmLaunch: bad geometry (c_pad %d, taps %d, passes %d)", args.c_pad, args.n_taps,
@@ -719,10 +819,19 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args, cudaStre
     SetError("GemmLaunch: output row stride %lld is not a multiple of 4", (long long)args.ld_out);
     return CE_GPU_EINVAL;
   }
-  switch (kind) {
-    case kKindI8: return LaunchKind<kKindI8>(ops, args, s);
-    case kKindBF16: return LaunchKind<kKindBF16>(ops, args, s);
-    case kKindTF32: return LaunchKind<kKindTF32>(ops, args, s);
+  static const int cta_group = getenv("CE_GPU_CTA_GROUP") ? atoi(getenv("CE_GPU_CTA_GROUP")) : 2;
+  if (cta_group == 1) {
+    switch (kind) {
+      case kKindI8: return LaunchKind<kKindI8, 1>(ops, args, s);
+      case kKindBF16: return LaunchKind<kKindBF16, 1>(ops, args, s);
+      case kKindTF32: return LaunchKind<kKindTF32, 1>(ops, args, s);
+    }
+  } else {
+    switch (kind) {
+      case kKindI8: return LaunchKind<kKindI8, 2>(ops, args, s);
+      case kKindBF16: return LaunchKind<kKindBF16, 2>(ops, args, s);
+      case kKindTF32: return LaunchKind<kKindTF32, 2>(ops, args, s);
+    }
   }
   SetError("GemmLaunch: unknown kind %d", kind);
   return CE_GPU_EINVAL;

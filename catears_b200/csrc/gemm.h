@@ -69,6 +69,9 @@ struct GemmArgs {
   int32_t n_store;               // columns written per row (>= N; columns [N, n_store) get 0) --
                                  // the zero padding of the next layer's K dimension
   int32_t round_tf32;            // out_f32 = tf32-rounded value (so that out_lo is exact)
+  int32_t debug;                 // CE_GPU_GEMM_DEBUG bits (timing probes only, results are WRONG):
+                                 // 1 = epilogue drains TMEM but skips math and stores,
+                                 // 2 = no tcgen05.mma is issued, 4 = no TMA loads are issued
 
   // fused FindMinMax (src/matrix.cc:329-345) for the next layer's Quantize: only rows the next
   // layer's Splice+Narrow actually reads take part.
