@@ -25,6 +25,7 @@ EXPORTS = [
     "ce_gpu_fbank", "ce_gpu_cmvn", "ce_gpu_rfft512", "ce_gpu_nnet", "ce_gpu_forward",
     "ce_gpu_nnet_keep_acc", "ce_gpu_nnet_get_acc", "ce_gpu_quantize", "ce_gpu_gemm_u8",
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
+    "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer",
     "ce_gpu_partition", "ce_gpu_time_shards",
 ]
 PROFILE_CATEGORIES = ["fbank", "cmvn", "gemm", "quantize", "finalize", "other"]
@@ -74,6 +75,10 @@ def lib():
     L.ce_gpu_time_shards.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, i64p, i64p, i64p, i64p]
     L.ce_gpu_profile_enable.argtypes = [C.c_int]
     L.ce_gpu_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.ce_gpu_selftest_quantizer.restype = C.c_int64
+    L.ce_gpu_selftest_quantizer.argtypes = [C.c_int64, C.c_uint64, C.c_int]
+    L.ce_gpu_profile_trace.argtypes = [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -132,6 +137,21 @@ def profile_read():
     n = (C.c_int64 * 6)()
     _check(lib().ce_gpu_profile_read(ms, n), "ce_gpu_profile_read")
     return {k: (ms[i], n[i]) for i, k in enumerate(PROFILE_CATEGORIES)}
+
+
+def selftest_quantizer(n=1 << 26, seed=1, device=0):
+    """Disagreements between the production quantiser arithmetic and plain IEEE (0 = exact)."""
+    return _check(lib().ce_gpu_selftest_quantizer(n, seed, device), "ce_gpu_selftest_quantizer")
+
+
+def profile_trace(cap=65536):
+    """[(category, begin_ms, end_ms)] of every timed launch scope since the last read, in launch
+    order; times share one clock across the chunk streams."""
+    cat = (C.c_int32 * cap)()
+    t0 = (C.c_double * cap)()
+    t1 = (C.c_double * cap)()
+    n = _check(lib().ce_gpu_profile_trace(cap, cat, t0, t1), "ce_gpu_profile_trace")
+    return [(PROFILE_CATEGORIES[cat[i]], t0[i], t1[i]) for i in range(n)]
 
 
 def frame_offsets(sample_offsets):

@@ -85,6 +85,14 @@ int ce_gpu_profile_read(double *ms, int64_t *launches) {
   return ProfRead(ms, launches);
 }
 
+int ce_gpu_profile_trace(int cap, int32_t *cat, double *t0_ms, double *t1_ms) {
+  if (cap < 0 || !cat || !t0_ms || !t1_ms) {
+    SetError("ce_gpu_profile_trace: bad arguments");
+    return CE_GPU_EINVAL;
+  }
+  return ProfTrace(cap, cat, t0_ms, t1_ms);
+}
+
 // ---- model ----------------------------------------------------------------------------
 
 ce_gpu_model_t *ce_gpu_model_load(const char *nnet_path, const char *prior_path,
@@ -319,12 +327,10 @@ int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sam
   CE_CHECK(UseDevice(m->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t base = utt_sample_offsets[0], total_samples = utt_sample_offsets[n_utts];
-  const void *pcm_dev = nullptr;
-  CE_CHECK(StageIn(pcm + base, sizeof(int16_t) * (size_t)(total_samples - base), &m->stage_pcm, s, &pcm_dev));
   std::vector<int64_t> soff(n_utts + 1);
   for (int u = 0; u <= n_utts; ++u) soff[u] = utt_sample_offsets[u] - base;
-  return PcmForward(m, static_cast<const int16_t *>(pcm_dev), total_samples - base, soff.data(),
-                    foff.data(), n_utts, loglik, argmax, s);
+  return PcmForward(m, pcm + base, total_samples - base, soff.data(), foff.data(), n_utts, loglik,
+                    argmax, s);
 }
 
 int ce_gpu_nnet_keep_acc(ce_gpu_model_t *m, int linear_ordinal) {
@@ -420,7 +426,8 @@ int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, floa
   StageWs *ws = GetWs(device);
   const void *x = nullptr;
   CE_CHECK(StageIn(src, sizeof(float) * (size_t)rows * cols, &ws->in, s, &x));
-  const int c_pad = RoundUp(cols, 4);
+  // the production kernel wants 128-column padding; odd widths take the generic one
+  const int c_pad = (cols % 4 == 0 && cols <= 1024) ? RoundUp(cols, 128) : RoundUp(cols, 4);
   CE_CHECK(ws->tmp[0].Reserve(sizeof(uint32_t) * 2));
   CE_CHECK(ws->tmp[1].Reserve(sizeof(QParam)));
   CE_CHECK(ws->tmp[2].Reserve((size_t)rows * c_pad));
@@ -429,9 +436,9 @@ int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, floa
   CE_CHECK(InitMinMaxLaunch(ws->tmp[0].as<uint32_t>(), 1, s));
   CE_CHECK(MinMaxLaunch(static_cast<const float *>(x), cols, cols, (int)rows, nullptr, nullptr, use,
                         ws->tmp[0].as<uint32_t>(), s));
-  CE_CHECK(QParamsLaunch(ws->tmp[0].as<uint32_t>(), ws->tmp[1].as<QParam>(), 1, s));
   CE_CHECK(QuantizeLaunch(static_cast<const float *>(x), cols, cols, (int)rows, c_pad, nullptr,
-                          ws->tmp[1].as<QParam>(), ws->tmp[2].as<uint8_t>(), nullptr, s));
+                          ws->tmp[0].as<uint32_t>(), 1, ws->tmp[1].as<QParam>(),
+                          ws->tmp[2].as<uint8_t>(), nullptr, s));
   QParam q;
   CE_CUDA(cudaMemcpyAsync(&q, ws->tmp[1].ptr, sizeof(q), cudaMemcpyDeviceToHost, s));
   CE_CUDA(cudaMemcpy2DAsync(dst, cols, ws->tmp[2].ptr, c_pad, cols, rows,
@@ -440,6 +447,21 @@ int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, floa
   if (scale) *scale = q.scale;
   if (zero_point) *zero_point = q.zero_point;
   return CE_GPU_OK;
+}
+
+int64_t ce_gpu_selftest_quantizer(int64_t n, uint64_t seed, int device) {
+  if (n <= 0) {
+    SetError("ce_gpu_selftest_quantizer: n must be positive");
+    return CE_GPU_EINVAL;
+  }
+  CE_CHECK(UseDevice(device));
+  StageWs *ws = GetWs(device);
+  CE_CHECK(ws->tmp[0].Reserve(sizeof(unsigned long long)));
+  CE_CUDA(cudaMemset(ws->tmp[0].ptr, 0, sizeof(unsigned long long)));
+  CE_CHECK(QuantSelfTestLaunch(n, seed, ws->tmp[0].as<unsigned long long>(), nullptr));
+  unsigned long long bad = 0;
+  CE_CUDA(cudaMemcpy(&bad, ws->tmp[0].ptr, sizeof(bad), cudaMemcpyDeviceToHost));
+  return (int64_t)bad;
 }
 
 int ce_gpu_gemm_u8(const uint8_t *a, float scale_a, int32_t zp_a, const uint8_t *b, float scale_b,

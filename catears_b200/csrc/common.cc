@@ -86,6 +86,29 @@ int ProfRead(double *ms, int64_t *launches) {
   return CE_GPU_OK;
 }
 
+int ProfTrace(int cap, int32_t *cat, double *t0_ms, double *t1_ms) {
+  int n = 0;
+  cudaEvent_t base = g_prof_recs.empty() ? nullptr : g_prof_recs.front().e0;
+  for (ProfRec &r : g_prof_recs) {
+    CE_CUDA(cudaEventSynchronize(r.e1));
+    if (n < cap) {
+      float a = 0.0f, b = 0.0f;
+      CE_CUDA(cudaEventElapsedTime(&a, base, r.e0));
+      CE_CUDA(cudaEventElapsedTime(&b, base, r.e1));
+      cat[n] = r.cat;
+      t0_ms[n] = a;
+      t1_ms[n] = b;
+      ++n;
+    }
+  }
+  for (ProfRec &r : g_prof_recs) {
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  return n;
+}
+
 int DeviceCount() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

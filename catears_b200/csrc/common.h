@@ -61,6 +61,9 @@ struct ProfScope {   // CUDA events around the launches made while it is alive (
 void ProfEnable(bool on);
 // Waits for the recorded launches, adds their times (ms) and counts per category, clears them.
 int ProfRead(double *ms, int64_t *launches);
+// Per-scope begin/end times (ms, relative to the first recorded scope) in launch order; returns the
+// number of records written (<= cap) or a negative error, and clears the records.
+int ProfTrace(int cap, int32_t *cat, double *t0_ms, double *t1_ms);
 
 // -- device selection -----------------------------------------------------------
 // Makes `device` current; fails with CE_GPU_ENODEVICE when there is none / not sm_100.

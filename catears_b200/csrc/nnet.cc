@@ -40,6 +40,9 @@ ce_gpu_model::~ce_gpu_model() {
   stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
   ws[0].Free(); ws[1].Free();
   if (inputs_ready) cudaEventDestroy(inputs_ready);
+  if (call_start) cudaEventDestroy(call_start);
+  for (cudaEvent_t e : copy_done) cudaEventDestroy(e);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
 namespace ce {
@@ -194,6 +197,8 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     CE_CUDA(cudaEventCreateWithFlags(&m->ws[i].to_lo, cudaEventDisableTiming));
   }
   CE_CUDA(cudaEventCreateWithFlags(&m->inputs_ready, cudaEventDisableTiming));
+  CE_CUDA(cudaEventCreateWithFlags(&m->call_start, cudaEventDisableTiming));
+  CE_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   return CE_GPU_OK;
 }
 
@@ -218,6 +223,7 @@ RowUse MakeRowUse(const ce_gpu_model *m, int producer /* -1 = network input */) 
 // the bases of the whole batch's outputs.
 struct PcmSource {
   const int16_t *pcm_dev = nullptr;     // nullptr: features are given
+  const int16_t *pcm_host = nullptr;    // set: pcm_dev is a staging buffer filled chunk by chunk
   int64_t total_samples = 0;
   const int64_t *sample_off = nullptr;  // [n_utts + 1] of this chunk
 };
@@ -311,9 +317,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   if (m->kind == kKindI8) {
     CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
     CE_CHECK(MinMaxLaunch(w->x0.as<float>(), F, F, M, d_tile, d_utts, MakeRowUse(m, -1), mm, s));
-    CE_CHECK(QParamsLaunch(mm, qp, n_utts, s));
-    CE_CHECK(QuantizeLaunch(w->x0.as<float>(), F, F, M, c0, d_tile, qp, w->act_u8.as<uint8_t>(),
-                            w->rowsum.as<int32_t>(), s));
+    CE_CHECK(QuantizeLaunch(w->x0.as<float>(), F, F, M, c0, d_tile, mm, n_utts, qp,
+                            w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
   } else if (m->kind == kKindBF16) {
     CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, w->act_bf16[0].as<__nv_bfloat16>(),
                            nullptr, nullptr, s));
@@ -428,8 +433,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
 
     if (m->kind == kKindI8 && !last) {
       QParam *q_next = qp + (size_t)(b + 1) * n_utts;
-      CE_CHECK(QParamsLaunch(mm + 2 * (size_t)(b + 1) * n_utts, q_next, n_utts, s));
-      CE_CHECK(QuantizeLaunch(w->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile, q_next,
+      CE_CHECK(QuantizeLaunch(w->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile,
+                              mm + 2 * (size_t)(b + 1) * n_utts, n_utts, q_next,
                               w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
     }
   }
@@ -454,6 +459,10 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   const bool am_host = argmax && !IsDevicePtr(argmax);
   const bool overlap = m->overlap && m->keep_acc < 0;
   if (overlap) CE_CUDA(cudaEventRecord(m->inputs_ready, s));
+  if (all.pcm_host) {                                    // the staging buffer is free once the work
+    CE_CUDA(cudaEventRecord(m->call_start, s));          // already queued on s has run
+    CE_CUDA(cudaStreamWaitEvent(m->copy_stream, m->call_start, 0));
+  }
   bool used[2] = {false, false};
   int u0 = 0, chunk = 0;
   while (u0 < n_utts) {
@@ -485,6 +494,17 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     }
     PcmSource src = all;
     if (all.pcm_dev) src.sample_off = all.sample_off + u0;
+    if (all.pcm_host && all.sample_off[u1] > all.sample_off[u0]) {
+      if ((int)m->copy_done.size() <= chunk) {
+        m->copy_done.resize(chunk + 1, nullptr);
+      }
+      if (!m->copy_done[chunk]) CE_CUDA(cudaEventCreateWithFlags(&m->copy_done[chunk], cudaEventDisableTiming));
+      const int64_t a = all.sample_off[u0], b = all.sample_off[u1];
+      CE_CUDA(cudaMemcpyAsync(const_cast<int16_t *>(all.pcm_dev) + a, all.pcm_host + a,
+                              sizeof(int16_t) * (size_t)(b - a), cudaMemcpyHostToDevice, m->copy_stream));
+      CE_CUDA(cudaEventRecord(m->copy_done[chunk], m->copy_stream));
+      CE_CUDA(cudaStreamWaitEvent(cs, m->copy_done[chunk], 0));
+    }
     CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
                           overlap ? w->stream_hi : cs));
     if (ll_host && nf > 0) {
@@ -515,11 +535,17 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
   return ForwardAll(m, PcmSource(), feats_dev, frame_off, n_utts, apply_cmvn, loglik, argmax, s);
 }
 
-int PcmForward(ce_gpu_model *m, const int16_t *pcm_dev, int64_t total_samples,
+int PcmForward(ce_gpu_model *m, const int16_t *pcm, int64_t total_samples,
                const int64_t *sample_off, const int64_t *frame_off, int n_utts, float *loglik,
                int32_t *argmax, cudaStream_t s) {
   PcmSource src;
-  src.pcm_dev = pcm_dev;
+  if (IsDevicePtr(pcm)) {
+    src.pcm_dev = pcm;
+  } else {
+    CE_CHECK(m->stage_pcm.Reserve(sizeof(int16_t) * (size_t)total_samples));
+    src.pcm_dev = m->stage_pcm.as<int16_t>();
+    src.pcm_host = pcm;
+  }
   src.total_samples = total_samples;
   src.sample_off = sample_off;
   return ForwardAll(m, src, nullptr, frame_off, n_utts, m->has_cmvn, loglik, argmax, s);

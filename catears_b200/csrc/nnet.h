@@ -37,7 +37,10 @@ struct ce_gpu_model {
   bool has_cmvn = false;
   std::vector<float> cmvn_host;   // num_mel sums + count
   ce::DevBuf cmvn_dev;
-  int64_t max_chunk_rows = 65536;
+  // Rows of activations evaluated per pass of the layer stack (CE_GPU_CHUNK_ROWS).  Large chunks
+  // amortise the per-launch ramp and tail of every kernel; a batch above the cap runs as several
+  // chunks, which is also the granularity at which host PCM is copied in behind the compute.
+  int64_t max_chunk_rows = 131072;
 
   // ---- workspace (one forward call at a time per handle) ----
   ce::DevBuf stage_pcm, stage_feats;
@@ -63,7 +66,15 @@ struct ce_gpu_model {
   };
   ChunkWs ws[2];
   cudaEvent_t inputs_ready = nullptr;
-  bool overlap = true;                 // CE_GPU_OVERLAP=0 runs every chunk on the caller's stream
+  // CE_GPU_OVERLAP=1 alternates chunks between the two workspaces on two internal streams.  Off by
+  // default: the GEMMs and the memory-bound kernels contend for the same L2 bandwidth, so running
+  // them side by side was measured to be no faster than back to back (overlap study).
+  bool overlap = false;
+  // Host PCM is copied chunk by chunk on its own stream so that chunk k+1 arrives while chunk k
+  // is being computed.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t call_start = nullptr;
+  std::vector<cudaEvent_t> copy_done;
   ce::DevBuf acc_dump;
 
   // ---- debug: kept accumulators ----
@@ -92,8 +103,10 @@ int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_of
                 bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s);
 
 // The whole path from PCM: like NnetForward, but every chunk first runs the fbank kernel on its
-// own utterances (pcm_dev / sample_off as in ce_gpu_fbank), on the chunk's stream.
-int PcmForward(ce_gpu_model *m, const int16_t *pcm_dev, int64_t total_samples,
+// own utterances (sample_off as in ce_gpu_fbank).  `pcm` is a device pointer or a host pointer;
+// host PCM is copied in chunk by chunk on the model's copy stream, behind the previous chunk's
+// compute.
+int PcmForward(ce_gpu_model *m, const int16_t *pcm, int64_t total_samples,
                const int64_t *sample_off, const int64_t *frame_off, int n_utts, float *loglik,
                int32_t *argmax, cudaStream_t s);
 

@@ -135,6 +135,192 @@ quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Quantize, the production form.  The kernel has to run BESIDE the persistent GEMM CTAs of the other
+// chunk stream, which leave about 24 K registers and 1.7 K thread slots per SM: too few warps to
+// cover HBM latency with one row per warp in flight.  So every warp keeps TWO rows (2 x NV x 16 B
+// per lane, 8 KB per warp for 1024 columns) in flight, a block is 4 warps at <= 96 registers (two
+// blocks fit beside a GEMM CTA = 64 KB in flight per SM), and the instruction stream is short:
+// the division by the per-utterance scale is done with the correctly rounded reciprocal and two
+// fused residual corrections (Markstein), which returns RN(v / scale) exactly as the reference's
+// `val / scale` does, in 5 instructions instead of the ~11 of a general IEEE division.
+// ComputeQuantizationParams (src/matrix.cc:348-362) is evaluated in the same kernel from the
+// min/max the producing GEMM reduced, and published for the consuming GEMM's epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQuantWarps = 4;
+constexpr int kQuantRowsPerWarp = 4;
+constexpr int kQuantUnitRows = kQuantWarps * kQuantRowsPerWarp;   // 16
+
+__device__ __forceinline__ QParam QParamsFromMinMax(const uint32_t *__restrict__ mm) {
+  const float mn = FloatFromOrdered(mm[0]);
+  const float mx = FloatFromOrdered(mm[1]);
+  const double scale = (double)__fsub_rn(mx, mn) / 255.0;             // matrix.cc:354
+  const double fzp = (double)(-mn) / scale;                           // matrix.cc:357
+  QParam q;
+  q.zero_point = (int32_t)round(fzp);                                 // matrix.cc:358
+  q.scale = (float)scale;                                             // matrix.cc:361
+  return q;
+}
+
+struct QuantConst {
+  float scale, inv, zp;
+  bool fast;          // scale is comfortably normal: the reciprocal path is exact
+};
+
+__device__ __forceinline__ QuantConst MakeQuantConst(const QParam p) {
+  QuantConst k;
+  k.scale = p.scale;
+  k.zp = (float)p.zero_point;
+  k.fast = p.scale > 1e-18f && p.scale < 1e18f;                       // false for NaN / denormal / inf
+  k.inv = k.fast ? __frcp_rn(p.scale) : 0.0f;
+  return k;
+}
+
+// RN(v / scale): q0 = RN(v * RN(1/scale)) is within 2 ulp; one residual step makes it faithful and
+// the second one correctly rounded (Markstein's theorem; the residuals are exact FMAs because
+// |v| <= 255 * scale * (1 + eps) keeps every term in the normal range, and for |v / scale| < 0.4
+// any last-bit error is absorbed by the rounding to an integer code).
+__device__ __forceinline__ float DivByScale(float v, const QuantConst &k) {
+  float q = __fmul_rn(v, k.inv);
+  float r = __fmaf_rn(-q, k.scale, v);
+  q = __fmaf_rn(r, k.inv, q);
+  r = __fmaf_rn(-q, k.scale, v);
+  return __fmaf_rn(r, k.inv, q);
+}
+
+// roundf(min(max(q, 0), 255)) as an int in [.., ..] BEFORE saturation: rounding half away from zero
+// commutes with the clamp (monotone, 0 and 255 are fixed points), truncating q + 0.49999997f is
+// round-half-away for 0 <= q < 2^23, negative / NaN inputs end at <= 0 and huge ones saturate.
+template <bool FAST>
+__device__ __forceinline__ int32_t CodeOf(float v, const QuantConst &k) {
+  const float d = FAST ? DivByScale(v, k) : __fdiv_rn(v, k.scale);    // matrix.cc:383
+  const float q = __fadd_rn(d, k.zp);
+  return __float2int_rz(__fadd_rn(q, 0.49999997f));                   // matrix.cc:384-385
+}
+
+__device__ __forceinline__ uint32_t PackCodes(int32_t a, int32_t b, int32_t c, int32_t d) {
+  uint32_t hi, w;   // bytes (low to high): a, b, c, d, each saturated to [0, 255]
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b), "r"(a), "r"(hi));
+  return w;
+}
+
+// One row held in registers -> NV words of codes per lane; returns this lane's share of the row sum.
+template <int NV, bool FAST>
+__device__ __forceinline__ int32_t QuantRow(const float4 (&v)[NV], const QuantConst &k, int C, int c_pad,
+                                            int lane, uint32_t *__restrict__ o) {
+  int32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c4 = (j * 32 + lane) * 4;
+    uint32_t w = 0;
+    if (c4 < C) {
+      w = PackCodes(CodeOf<FAST>(v[j].x, k), CodeOf<FAST>(v[j].y, k), CodeOf<FAST>(v[j].z, k),
+                    CodeOf<FAST>(v[j].w, k));
+      sum = (int32_t)__dp4a(w, 0x01010101u, (uint32_t)sum);
+    }
+    if (c4 < c_pad) o[j * 32 + lane] = w;
+  }
+  return sum;
+}
+
+template <int NV>
+__global__ void __maxnreg__(96)
+quantize_rows_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_pad,
+                     const int32_t *__restrict__ tile_utt, const uint32_t *__restrict__ minmax,
+                     QParam *__restrict__ qp, uint8_t *__restrict__ q, int32_t *__restrict__ rowsum) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_units = (M + kQuantUnitRows - 1) / kQuantUnitRows;
+  // contiguous unit range of this block
+  const int u_begin = (int)((int64_t)n_units * blockIdx.x / gridDim.x);
+  const int u_end = (int)((int64_t)n_units * (blockIdx.x + 1) / gridDim.x);
+  const int n_rows = (u_end - u_begin) * kQuantRowsPerWarp;           // rows of this warp
+  if (n_rows <= 0) return;
+  auto row_of = [&](int i) {
+    return (u_begin + i / kQuantRowsPerWarp) * kQuantUnitRows + warp * kQuantRowsPerWarp +
+           (i % kQuantRowsPerWarp);
+  };
+  auto load_row = [&](int row, float4 (&buf)[NV]) {
+    const float *r = x + (int64_t)row * ld_in;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = (i * 32 + lane) * 4;
+      buf[i] = (row < M && c4 < C) ? __ldcs(reinterpret_cast<const float4 *>(r + c4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  float4 cur[NV], nxt[NV];
+  load_row(row_of(0), cur);
+  int utt_cached = -1;
+  QuantConst k = {1.0f, 1.0f, 0.0f, false};
+  for (int i = 0; i < n_rows; ++i) {
+    const int row = row_of(i);
+    if (i + 1 < n_rows) load_row(row_of(i + 1), nxt);
+    if (row < M) {
+      const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+      if (utt != utt_cached) {                                       // warp-uniform
+        QParam p;
+        if (minmax) {
+          p = QParamsFromMinMax(minmax + 2 * utt);
+          if (lane == 0) qp[utt] = p;                                // same value from every writer
+        } else {
+          p = qp[utt];
+        }
+        k = MakeQuantConst(p);
+        utt_cached = utt;
+      }
+      uint32_t *o = reinterpret_cast<uint32_t *>(q + (int64_t)row * c_pad);
+      const int32_t sum = k.fast ? QuantRow<NV, true>(cur, k, C, c_pad, lane, o)     // warp-uniform
+                                 : QuantRow<NV, false>(cur, k, C, c_pad, lane, o);
+      int32_t tot = sum;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+      if (lane == 0 && rowsum) rowsum[row] = tot;
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) cur[j] = nxt[j];
+  }
+}
+
+// Self-test of the reciprocal division against the IEEE division, and of the packed rounding
+// against roundf: counts (v, scale) pairs whose codes differ.
+__global__ void quant_selftest_kernel(int64_t n, uint64_t seed, unsigned long long *mismatches) {
+  unsigned long long bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    // scale: random mantissa, exponent in [-40, 40]; v: scale * code-ish value with random low bits
+    const uint32_t mant = (uint32_t)z & 0x7fffffu;
+    const int e = (int)((z >> 23) % 81) - 40;
+    const float scale = __uint_as_float(((uint32_t)(127 + e) << 23) | mant);
+    const uint32_t r2 = (uint32_t)(z >> 32);
+    const int mode = r2 & 3;
+    float t;                                              // target quotient
+    if (mode == 0) t = (float)(r2 >> 8) * (300.0f / 16777216.0f) - 20.0f;            // uniform [-20, 280)
+    else if (mode == 1) t = (float)((r2 >> 8) & 255) + 0.5f;                          // near the ties
+    else if (mode == 2) t = (float)((r2 >> 8) & 255) + 0.5f + ((int)((r2 >> 16) & 15) - 8) * 1e-5f;
+    else t = __uint_as_float((r2 & 0x7fffffffu) % 0x43800000u);                        // any float in [0, 256)
+    float v = __fmul_rn(t, scale);
+    if (v != 0.0f) v = __uint_as_float(__float_as_uint(v) + ((r2 >> 5) & 3) - 1);    // +-1 ulp jitter
+    QParam p;
+    p.scale = scale;
+    p.zero_point = (int32_t)((z >> 40) & 255);
+    const QuantConst k = MakeQuantConst(p);
+    const uint32_t got = (k.fast ? PackCodes(CodeOf<true>(v, k), 0, 0, 0)
+                                : PackCodes(CodeOf<false>(v, k), 0, 0, 0)) & 255u;
+    const uint32_t want = QuantOne(v, scale, (float)p.zero_point);
+    if (got != want) ++bad;
+    // the quotient itself, wherever it can matter for a code (|v / scale| >= 1/4)
+    const float ref = __fdiv_rn(v, scale);
+    if (k.fast && fabsf(ref) >= 0.25f && fabsf(ref) < 1e6f && DivByScale(v, k) != ref) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 __device__ __forceinline__ float RoundTf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -328,15 +514,42 @@ int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s) {
 }
 
 int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const int32_t *tile_utt,
-                   const QParam *qp, uint8_t *q, int32_t *rowsum, cudaStream_t s) {
+                   const uint32_t *minmax, int n_utts, QParam *qp, uint8_t *q, int32_t *rowsum,
+                   cudaStream_t s) {
   if (M <= 0) return CE_GPU_OK;
   if (c_pad % 4 != 0) {
     SetError("QuantizeLaunch: c_pad %d is not a multiple of 4", c_pad);
     return CE_GPU_EINVAL;
   }
+  const bool rows_path = c_pad % 128 == 0 && c_pad <= 1024 && C % 4 == 0 && ld_in % 4 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (!rows_path) {                                      // odd shapes: one row per warp, generic loads
+    if (minmax) CE_CHECK(QParamsLaunch(minmax, qp, n_utts, s));
+    ProfScope prof(kProfQuantize, s);
+    const unsigned grid = (unsigned)std::min((M + 7) / 8, 32 * SmCount());
+    quantize_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
+    CE_LAUNCHED();
+    return CE_GPU_OK;
+  }
   ProfScope prof(kProfQuantize, s);
-  const unsigned grid = (unsigned)std::min((M + 7) / 8, 32 * SmCount());
-  quantize_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt, qp, q, rowsum);
+  const int n_units = (M + kQuantUnitRows - 1) / kQuantUnitRows;
+  static const int per_sm = getenv("CE_GPU_QUANT_GRID") ? atoi(getenv("CE_GPU_QUANT_GRID")) : 4;
+  const unsigned grid = (unsigned)std::min(n_units, per_sm * SmCount());
+#define CE_QUANT_ROWS(NV)                                                                       \
+  quantize_rows_kernel<NV><<<grid, 32 * kQuantWarps, 0, s>>>(x, ld_in, C, M, c_pad, tile_utt,   \
+                                                              minmax, qp, q, rowsum)
+  const int nv = c_pad / 128;
+  if (nv <= 1) { CE_QUANT_ROWS(1); }
+  else if (nv <= 2) { CE_QUANT_ROWS(2); }
+  else if (nv <= 4) { CE_QUANT_ROWS(4); }
+  else { CE_QUANT_ROWS(8); }
+#undef CE_QUANT_ROWS
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
+
+int QuantSelfTestLaunch(int64_t n, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t s) {
+  quant_selftest_kernel<<<4 * SmCount(), 256, 0, s>>>(n, seed, mismatches_dev);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

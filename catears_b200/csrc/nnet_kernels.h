@@ -19,8 +19,15 @@ int InitMinMaxLaunch(uint32_t *mm, int n_pairs, cudaStream_t s);
 int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_utt,
                  const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s);
 int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s);
+// Quantize of x [M x ld_in] (C columns) into q [M x c_pad] (+ row sums of the codes).  With
+// `minmax` ([n_utts][2], the reduced FindMinMax) the parameters are computed in the same launch and
+// written to qp; with minmax == nullptr qp is the input.
 int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const int32_t *tile_utt,
-                   const QParam *qp, uint8_t *q, int32_t *rowsum, cudaStream_t s);
+                   const uint32_t *minmax, int n_utts, QParam *qp, uint8_t *q, int32_t *rowsum,
+                   cudaStream_t s);
+// Counts disagreements between the production quantiser arithmetic and the plain IEEE form over n
+// pseudo-random (value, scale, zero point) triples (adds to *mismatches_dev).
+int QuantSelfTestLaunch(int64_t n, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t s);
 int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
                   __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s);
 int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,

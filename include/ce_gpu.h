@@ -136,6 +136,13 @@ int ce_gpu_nnet_get_acc(ce_gpu_model_t *m, int utt, int32_t *acc, int64_t cap, i
 int ce_gpu_quantize(const float *src, int64_t rows, int cols, uint8_t *dst, float *scale,
                     int32_t *zero_point, int device, void *stream);
 
+/* Device self-test of the quantiser's arithmetic: the production kernel divides by the scale with
+ * a correctly rounded reciprocal and two fused corrections and rounds by truncating
+ * q + 0.49999997f; this compares it with `roundf(min(max(v / scale + zp, 0), 255))` in plain IEEE
+ * operations over n pseudo-random triples concentrated on the rounding ties.  Returns the number
+ * of disagreements (0 = bit-exact) or a negative error. */
+int64_t ce_gpu_selftest_quantizer(int64_t n, uint64_t seed, int device);
+
 /* MatMat_U8U8F32 (src/matrix.cc:389-420): A[m x k] u8, B[k x n] u8, both row-major;
  * C[m x n] = (float)acc * (scale_a*scale_b), acc = sum_k (A-zp_a)(B-zp_b) in int32.
  * acc (nullable) receives the int32 accumulators. */
@@ -176,6 +183,11 @@ int64_t ce_gpu_launch_count(int reset);
 #define CE_GPU_PROFILE_CATEGORIES 6
 int ce_gpu_profile_enable(int on);
 int ce_gpu_profile_read(double *ms, int64_t *launches);
+/* Instead of the sums: one record per timed launch scope, in launch order -- category and
+ * begin/end in milliseconds relative to the first record (events of different streams share one
+ * clock, so this is a timeline of the overlapped chunk streams).  Returns the number of records
+ * written (<= cap) or a negative error; clears the records like ce_gpu_profile_read. */
+int ce_gpu_profile_trace(int cap, int32_t *cat, double *t0_ms, double *t1_ms);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,35 @@ def test_quantize_vs_oracle_shapes(port):
         assert np.array_equal(q, wq), shape
 
 
+def test_quantizer_arithmetic_selftest():
+    """The production quantiser (reciprocal + two fused corrections, truncation of q + 0.49999997,
+    saturating pack) against plain IEEE `roundf(min(max(v / scale + zp, 0), 255))` on the device:
+    2^27 triples concentrated on the rounding ties, zero disagreements allowed."""
+    for seed in (1, 2026):
+        assert api.selftest_quantizer(1 << 26, seed) == 0
+
+
+def test_quantize_wide_rows_vs_oracle(port):
+    """Shapes that take the two-rows-in-flight kernel (cols % 4 == 0, <= 1024), incl. a degenerate
+    all-zero matrix (denormal scale -> the plain-division branch) and ragged row counts."""
+    rng = np.random.default_rng(11)
+    for shape in ((1, 4), (17, 40), (33, 128), (250, 200), (1000, 1024), (3, 512)):
+        x = (rng.standard_normal(shape) * rng.uniform(0.1, 50)).astype(np.float32)
+        x[rng.random(shape) < 0.3] = 0.0
+        q, s, z = api.quantize(x)
+        wq, ws, wz = port.quantize(x)
+        assert (s, z) == (ws, wz), shape
+        assert np.array_equal(q, wq), shape
+    x = np.zeros((9, 64), np.float32)
+    q, s, z = api.quantize(x)
+    wq, ws, wz = port.quantize(x)
+    assert (s, z) == (ws, wz) and np.array_equal(q, wq)
+    x = -np.abs(rng.standard_normal((40, 256))).astype(np.float32)
+    q, s, z = api.quantize(x)
+    wq, ws, wz = port.quantize(x)
+    assert (s, z) == (ws, wz) and np.array_equal(q, wq)
+
+
 def test_gemm_u8_reference_vectors(golden):
     r = golden["ref"]
     sa, za, sb, zb = r["q_params"]

@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Timeline of one overlapped step (ce_gpu_profile_trace): per category busy time, the union of
+the busy intervals, and how much of the GEMM time had a memory-bound kernel running beside it."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from catears_b200 import api, synth  # noqa: E402
+
+
+def union(iv):
+    iv = sorted(iv)
+    tot, cur_a, cur_b = 0.0, None, None
+    for a, b in iv:
+        if cur_b is None or a > cur_b:
+            if cur_b is not None:
+                tot += cur_b - cur_a
+            cur_a, cur_b = a, b
+        else:
+            cur_b = max(cur_b, b)
+    if cur_b is not None:
+        tot += cur_b - cur_a
+    return tot
+
+
+def main():
+    import torch
+    n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    conf = os.path.join(bench.model_dir(), "tdnn.conf")
+    pcm, off = synth.synth_batch(n_utts, 160000)
+    model = api.AcousticModelGpu(config=conf, precision="int8")
+    d_pcm = torch.from_numpy(pcm).cuda()
+    frames = int(api.frame_offsets(off)[-1])
+    d_ll = torch.empty((frames, model.num_pdfs), dtype=torch.float32, device="cuda")
+    d_am = torch.empty(frames, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream()
+    for _ in range(3):
+        model.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=s)
+    torch.cuda.synchronize()
+    api.profile_enable(True)
+    model.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=s)
+    torch.cuda.synchronize()
+    tr = api.profile_trace()
+    api.profile_enable(False)
+    t_end = max(t[2] for t in tr)
+    print("records %d, span %.3f ms" % (len(tr), t_end))
+    by = {}
+    for c, a, b in tr:
+        by.setdefault(c, []).append((a, b))
+    for c, iv in by.items():
+        print("  %-9s n=%4d sum %.3f ms union %.3f ms" % (c, len(iv), sum(b - a for a, b in iv), union(iv)))
+    print("  union of everything %.3f ms" % union([(a, b) for _, a, b in tr]))
+    if len(sys.argv) > 2:
+        for c, a, b in tr[:int(sys.argv[2])]:
+            print("    %-9s %9.3f -> %9.3f  (%.1f us)" % (c, a, b, 1e3 * (b - a)))
+
+
+if __name__ == "__main__":
+    main()
