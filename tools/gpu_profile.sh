@@ -15,6 +15,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm
     -o gpurun_out/prof_gemm_${TAG} -f $SMALL > gpurun_out/ncu_gemm_${TAG}.log 2>&1
 echo "ncu gemm exit=$?"
 timeout 300 $SMALL > gpurun_out/plain3_${TAG}.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fbank_kernel|quantize_kernel|finalize_rowcache|cmvn_kernel" -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fbank_kernel|quantize_rows_kernel|finalize_rowcache|cmvn_kernel" -c 12 \
     -o gpurun_out/prof_misc_${TAG} -f $SMALL > gpurun_out/ncu_misc_${TAG}.log 2>&1
 echo "ncu misc exit=$?"
