@@ -7,11 +7,16 @@
 // and AcousticModel's edge replication (src/am.cc:119-124,152-155).
 //
 // The reference re-rounds the running sum to fp32 after every frame, so the chain is replayed
-// in order: one thread per (utterance, mel bin) walks the frames sequentially with
-// exactly the reference's operations (double add, float round; un-fused float multiply/add).
-// Parallelism comes from utterances x bins; the count / smoothing weight / 1/count depend only
-// on the frame index and are taken from a 600-entry table built on the host with the same
-// arithmetic.  Loads run one 16-frame batch ahead of the chain; a warp reads 128 contiguous bytes.
+// in order with exactly the reference's operations (double add, float round; un-fused float
+// multiply/add) and stays bit-exact at any utterance length.  Only that chain is
+// sequential -- four dependent operations per frame and bin -- so it is all the chain threads do:
+// one CTA owns one utterance and works on tiles of kTileFrames frames in a three-stage pipeline,
+//   loader/output warps   global -> shared memory for tile j+1 (x_t and x_{t-600}, coalesced),
+//                         y_t = x_t + nscale_t (S_t + alpha_t g) and the stores for tile j-1,
+//   chain warps           S_t for tile j, one thread per mel bin, operands read from shared memory
+//                         (independent of the chain, so their latency is hidden by unrolling).
+// The count / smoothing weight / 1/count depend only on the frame index and come from a
+// 600-entry table built on the host with the same arithmetic.
 //
 // HBM traffic: 4*mel bytes read + 4*mel written per frame (x_{t-600} is an L2 hit).
 
@@ -36,70 +41,140 @@ struct CmvnStep {    // frame-index-only part of the chain (t < 600; t >= 599 us
   float nscale;      // -(float)(1 / count_after_smoothing)
 };
 
-constexpr int kUnroll = 16;
+constexpr int kCmvnThreads = 256;
 
-// One thread per (utt, d), flattened so that warps stay full for any mel.
-__global__ void __launch_bounds__(128)
+// Shared memory: x[2][TF][mel], xo[2][TF][mel], S[2][TF][mel] floats.
+__global__ void __launch_bounds__(kCmvnThreads)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
-            int mel, int pad_left, int pad_right, float *__restrict__ out, int64_t out_stride) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int u = (int)(idx / mel);
-  const int d = (int)(idx % mel);
-  if (u >= n_utts) return;
-  const CmvnUtt ut = utts[u];
-  const float *x = feats + ut.in_row * mel + d;
-  float *y = out + (ut.out_row + pad_left) * out_stride + d;
+            int mel, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
+            int64_t out_stride) {
+  extern __shared__ float cmvn_smem[];
+  const CmvnUtt ut = utts[blockIdx.x];
   const int T = ut.T;
+  if (T <= 0) return;
+  const int TF = tile_frames;
+  const int tile_elems = TF * mel;
+  float *xs = cmvn_smem;                         // [2][tile_elems]
+  float *xos = cmvn_smem + 2 * tile_elems;       // [2][tile_elems]
+  float *ss = cmvn_smem + 4 * tile_elems;        // [2][tile_elems]
   const bool apply = g != nullptr;
-  const float gd = apply ? g[d] : 0.0f;
+  const int chain_threads = apply ? ((mel + 31) / 32) * 32 : 0;   // whole warps
+  const int tid = threadIdx.x;
+  const bool is_chain = tid < chain_threads;
+  const int wtid = tid - chain_threads;          // index among the loader/output threads
+  const int n_workers = kCmvnThreads - chain_threads;
+  const float *x = feats + ut.in_row * mel;
+  float *y = out + (ut.out_row + pad_left) * out_stride;
+  const int n_tiles = (T + TF - 1) / TF;
 
-  // Software pipeline: the loads of batch k+1 are in flight while the (sequential, rounding-
-  // exact) chain of batch k runs.
-  float cached = 0.0f, y_first = 0.0f, y_last = 0.0f;
-  float xv[kUnroll], xo[kUnroll];
-  auto load_batch = [&](int t0, float (&a)[kUnroll], float (&b)[kUnroll]) {
+  // Workers index a tile flat (it is contiguous in feats); i / mel by multiply-shift (i < 2^13,
+  // mel <= 128: exact with a 20-bit reciprocal).  Every load of a tile is issued before any is used.
+  const uint32_t inv_mel = ((1u << 20) + mel - 1) / mel;
+  constexpr int kPerThread = 16;                 // >= tile_elems / n_workers for every configuration
+  auto load_tile = [&](int j) {                  // workers: global -> smem, tile j
+    const int t0 = j * TF;
+    const int n = min(TF, T - t0) * mel;
+    float *dx = xs + (j & 1) * tile_elems;
+    float *dxo = xos + (j & 1) * tile_elems;
+    const float *src = x + (int64_t)t0 * mel;
+    const bool need_old = apply && t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
+    const int first_old = (kCmvnWindow - t0) * mel;         // elements before it have t < 600
+    float a[kPerThread], b[kPerThread];
 #pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      const int t = t0 + j;
-      a[j] = (t < T) ? __ldg(x + (int64_t)t * mel) : 0.0f;
-      b[j] = (apply && t < T && t >= kCmvnWindow) ? __ldg(x + (int64_t)(t - kCmvnWindow) * mel) : 0.0f;
+    for (int k = 0; k < kPerThread; ++k) {
+      const int i = wtid + k * n_workers;
+      a[k] = (i < n) ? __ldg(src + i) : 0.0f;
+      b[k] = (need_old && i < n && i >= first_old) ? __ldg(src + i - kCmvnWindow * mel) : 0.0f;
     }
-  };
-  load_batch(0, xv, xo);
-  for (int t0 = 0; t0 < T; t0 += kUnroll) {
-    float nv[kUnroll], no[kUnroll];
-    load_batch(t0 + kUnroll, nv, no);
 #pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      const int t = t0 + j;
-      if (t < T) {
-        float r = xv[j];
-        if (apply) {
-          double s = (double)cached;                       // cmvn.cc:42-47 (double accumulate)
-          s += (double)xv[j];
-          if (t >= kCmvnWindow) s += -1.0 * (double)xo[j];
-          cached = (float)s;                               // cmvn.cc:63-67 (stored as float)
-          const CmvnStep st = steps[min(t, kCmvnWindow - 1)];
-          float stat = cached;
-          if (t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, gd));   // AddVec
-          r = __fadd_rn(xv[j], __fmul_rn(st.nscale, stat));                          // cmvn.cc:96-97
-        }
-        y[(int64_t)t * out_stride] = r;
-        if (t == 0) y_first = r;
-        y_last = r;
+    for (int k = 0; k < kPerThread; ++k) {
+      const int i = wtid + k * n_workers;
+      if (i < n) {
+        dx[i] = a[k];
+        if (need_old) dxo[i] = b[k];
       }
     }
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-      xv[j] = nv[j];
-      xo[j] = no[j];
+  };
+  auto store_tile = [&](int j) {                 // workers: y for tile j, and the replicated edges
+    const int t0 = j * TF;
+    const int n = min(TF, T - t0) * mel;
+    const float *dx = xs + (j & 1) * tile_elems;
+    const float *ds = ss + (j & 1) * tile_elems;
+#pragma unroll 4
+    for (int i = wtid; i < n; i += n_workers) {
+      const int tl = (int)(((uint32_t)i * inv_mel) >> 20), d = i - tl * mel;
+      const int t = t0 + tl;
+      float r = dx[i];
+      if (apply) {
+        const CmvnStep st = steps[min(t, kCmvnWindow - 1)];
+        float stat = ds[i];
+        if (t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, __ldg(g + d)));   // AddVec
+        r = __fadd_rn(r, __fmul_rn(st.nscale, stat));                                       // cmvn.cc:96-97
+      }
+      y[(int64_t)t * out_stride + d] = r;
+      if (t == 0)
+        for (int p = 1; p <= pad_left; ++p) y[-(int64_t)p * out_stride + d] = r;
+      if (t == T - 1)
+        for (int p = 1; p <= pad_right; ++p) y[(int64_t)(T - 1 + p) * out_stride + d] = r;
     }
+  };
+
+  // The reference's  S = float(double(S) + x - x_old)  (cmvn.cc:42-47,63-67) without fp64, whose
+  // CUDA-core rate on this part makes a dependent chain cost ~280 clocks per frame: the double sums
+  // are exact (24-bit operands a few binades apart), so S is the correctly rounded three-term sum.
+  // With d = x - x_old: if the subtraction is exact (its TwoSum error term is zero -- always, for
+  // log-mel magnitudes) the result is RN(S + d), one fp32 add; otherwise fall back to fp64.  For
+  // t < 600 it is RN(S + x).  Only that add is on the dependent chain.
+  float cached = 0.0f;                           // chain state of this thread's bin
+  if (!is_chain) load_tile(0);
+  __syncthreads();
+  for (int j = 0; j < n_tiles; ++j) {
+    if (is_chain) {
+      if (tid < mel) {
+        const int t0 = j * TF;
+        const int nt = min(TF, T - t0);
+        const float *dx = xs + (j & 1) * tile_elems + tid;
+        const float *dxo = xos + (j & 1) * tile_elems + tid;
+        float *ds = ss + (j & 1) * tile_elems + tid;
+        if (t0 + TF <= kCmvnWindow) {            // no frame leaves the window yet
+#pragma unroll 8
+          for (int tl = 0; tl < nt; ++tl) {
+            cached = __fadd_rn(cached, dx[tl * mel]);
+            ds[tl * mel] = cached;
+          }
+        } else {
+#pragma unroll 8
+          for (int tl = 0; tl < nt; ++tl) {
+            const float xv = dx[tl * mel];
+            if (t0 + tl >= kCmvnWindow) {
+              const float xo = dxo[tl * mel];
+              const float dh = __fsub_rn(xv, xo);                      // TwoSum(x, -x_old)
+              const float bv = __fsub_rn(dh, xv);
+              const float dl = __fadd_rn(__fsub_rn(xv, __fsub_rn(dh, bv)), __fsub_rn(-xo, bv));
+              if (dl == 0.0f) {
+                cached = __fadd_rn(cached, dh);
+              } else {                                                 // inexact difference: as written
+                double s2 = (double)cached;
+                s2 += (double)xv;
+                s2 += -1.0 * (double)xo;
+                cached = (float)s2;
+              }
+            } else {
+              cached = __fadd_rn(cached, xv);
+            }
+            ds[tl * mel] = cached;
+          }
+        }
+      }
+    } else {
+      if (j > 0) store_tile(j - 1);              // reads buffers (j-1)&1 ...
+      asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory");
+      if (j + 1 < n_tiles) load_tile(j + 1);     // ... which tile j+1 then overwrites
+    }
+    __syncthreads();
   }
-  if (T > 0) {
-    for (int p = 0; p < pad_left; ++p) y[(int64_t)(p - pad_left) * out_stride] = y_first;
-    for (int p = 0; p < pad_right; ++p) y[(int64_t)(T + p) * out_stride] = y_last;
-  }
+  if (!is_chain) store_tile(n_tiles - 1);
 }
 
 struct StepTable {
@@ -164,11 +239,27 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
     h[u].pad = 0;
   }
   CE_CHECK(utts->Upload(bytes, s));
-  const int64_t n_threads = (int64_t)n_utts * num_mel;
-  const unsigned grid = (unsigned)((n_threads + 127) / 128);
+  if (num_mel > kMaxMel) {
+    SetError("CmvnLaunch: num_mel %d > %d", num_mel, kMaxMel);
+    return CE_GPU_EINVAL;
+  }
+  // frames per tile: the largest power of two whose tile the worker threads cover with 16 elements each
+  const int workers = kCmvnThreads - (global_stats_dev ? (num_mel + 31) / 32 * 32 : 0);
+  int tile_frames = 64;
+  while (tile_frames > 1 && tile_frames * num_mel > 16 * workers) tile_frames >>= 1;
+  const size_t smem = sizeof(float) * 6 * (size_t)tile_frames * num_mel;
+  static thread_local size_t configured[64] = {0};
+  int dev = 0;
+  CE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || smem > configured[dev]) {
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev < 64) configured[dev] = smem;
+  }
   ProfScope prof(kProfCmvn, s);
-  cmvn_kernel<<<grid, 128, 0, s>>>(global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(),
-                                     n_utts, num_mel, pad_left, pad_right, out_dev, out_stride);
+  cmvn_kernel<<<(unsigned)n_utts, kCmvnThreads, smem, s>>>(global_stats_dev, steps, feats_dev,
+                                                           utts->dev<CmvnUtt>(), n_utts, num_mel,
+                                                           tile_frames, pad_left, pad_right, out_dev,
+                                                           out_stride);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

@@ -468,10 +468,14 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   while (u0 < n_utts) {
     int u1 = u0;
     int64_t rows = 0;
+    // Host PCM arrives over PCIe behind the compute: a short first chunk (a quarter of the cap)
+    // keeps the copy nobody can hide short; every later copy runs under the previous chunk.
+    const int64_t cap = (all.pcm_host && chunk == 0) ? std::max<int64_t>(kTileM, m->max_chunk_rows / 4)
+                                                      : m->max_chunk_rows;
     while (u1 < n_utts) {
       const int64_t T = frame_off[u1 + 1] - frame_off[u1];
       const int64_t r = T > 0 ? (T + L + R + kTileM - 1) / kTileM * kTileM : 0;
-      if (u1 > u0 && rows + r > m->max_chunk_rows) break;
+      if (u1 > u0 && rows + r > cap) break;
       rows += r;
       ++u1;
     }

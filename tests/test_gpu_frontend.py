@@ -132,6 +132,25 @@ def test_cmvn_ragged_batch_bit_exact_vs_oracle(port, golden):
             assert np.array_equal(out[off[u]:off[u + 1]], want), n
 
 
+def test_cmvn_chain_exact_on_adversarial_values(port, golden):
+    """The kernel replaces the reference's fp64 accumulate by RN(S + (x - x_old)) whenever the
+    difference is exact and falls back to fp64 otherwise: mixed signs and magnitudes spread over
+    twelve decades (inexact differences, catastrophic cancellation, exact zeros) must still be
+    bit-identical to the in-order double chain of src/cmvn.cc:42-67, well past the 600-frame window."""
+    rng = np.random.default_rng(2026)
+    T = 1500
+    mag = 10.0 ** rng.uniform(-6, 6, size=(T, 40))
+    feats = (mag * rng.choice([-1.0, 1.0], size=(T, 40))).astype(np.float32)
+    feats[rng.random((T, 40)) < 0.05] = 0.0
+    feats[700:720] = feats[100:120]                  # x_t == x_{t-600}: exact zero differences
+    out = api.cmvn(golden["cmvn_stats"], feats)
+    assert np.array_equal(out, port.cmvn(golden["cmvn_stats"], feats))
+    # a long utterance of ordinary log-mel magnitudes (rounding drift over 4000 frames)
+    feats = (12.0 + 4.0 * rng.standard_normal((4000, 40))).astype(np.float32)
+    out = api.cmvn(golden["cmvn_stats"], feats)
+    assert np.array_equal(out, port.cmvn(golden["cmvn_stats"], feats))
+
+
 def test_cmvn_in_place_on_device(golden, port):
     import torch
     rng = np.random.default_rng(12)
