@@ -1,0 +1,119 @@
+// Drives include/ce_host.hpp the way src/ce_stt.cc:295-362 drives the reference's stage objects:
+// PCM in 1 KB pieces -> Fbank::Process -> [CMVN] -> AcousticModel::Process per frame ->
+// EndOfStream; the log-likelihood rows a decoder would consume are written to a file.
+//
+//   host_mirror_test errors
+//   host_mirror_test stream <conf> <pcm.s16le> <out.bin> <precision 0..3> [cmvn_stats.vec0]
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ce_host.hpp"
+
+using namespace ce_host;
+
+static int Fail(const char *what, const Status &st) {
+  fprintf(stderr, "FAIL %s: %s\n", what, st.what().c_str());
+  return 1;
+}
+
+static int Errors() {
+  AcousticModel am;
+  Status st = am.Read("/nonexistent/dir/model.conf");
+  if (st.ok() || st.what().empty()) return Fail("Read of a missing config must fail", st);
+  Matrix lp;
+  AcousticModel::Instance inst;
+  float frame[40] = {0};
+  st = am.Process(&inst, frame, &lp);
+  if (st.ok()) return Fail("Process before Read must fail", st);
+  std::vector<int32_t> v;
+  st = detail::ReadVec0<int32_t>("/nonexistent/file", &v);
+  if (st.ok()) return Fail("ReadVec0 of a missing file must fail", st);
+  if (ce_gpu_device_count() == 0) {                        // no CPU fallback behind the mirror
+    Fbank fb;
+    Fbank::Instance fi;
+    std::vector<int16_t> pcm(1600, 100);
+    Matrix feats;
+    st = fb.Process(&fi, pcm.data(), (int)pcm.size(), &feats);
+    if (st.ok() || st.what().find("no CUDA device") == std::string::npos)
+      return Fail("Fbank::Process without a device must report it", st);
+  }
+  Fbank fb;
+  Fbank::Instance fi;
+  Matrix feats;
+  std::vector<float> bad(500, 0.5f);                        // not int16-valued
+  st = fb.Process(&fi, bad, &feats);
+  if (st.ok()) return Fail("non-integral samples must be rejected", st);
+  printf("OK\n");
+  return 0;
+}
+
+static int Stream(int argc, char **argv) {
+  const std::string conf = argv[2], pcm_path = argv[3], out_path = argv[4];
+  const int precision = atoi(argv[5]);
+  AcousticModel am;
+  Status st = am.Read(conf, precision, 0);
+  if (!st.ok()) return Fail("AcousticModel::Read", st);
+  std::vector<float> stats;
+  if (argc > 6) {
+    st = detail::ReadVec0<float>(argv[6], &stats);
+    if (!st.ok()) return Fail("cmvn stats", st);
+  }
+  FILE *f = fopen(pcm_path.c_str(), "rb");
+  if (!f) return Fail("open pcm", Status::IOError(pcm_path));
+  Fbank fbank(am.feat_dim(), 0);
+  Fbank::Instance fbank_inst;
+  AcousticModel::Instance am_inst;
+  std::vector<float> rows;                                  // what Decoder::Process would receive
+  Matrix all_feats(0, am.feat_dim());
+  char buf[1024];                                           // src/main.cc:38-44 reads 1024-byte pieces
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) {
+    Matrix feats;
+    st = fbank.Process(&fbank_inst, reinterpret_cast<const int16_t *>(buf), (int)(got / 2), &feats);
+    if (!st.ok()) return Fail("Fbank::Process", st);
+    all_feats.data.insert(all_feats.data.end(), feats.data.begin(), feats.data.end());
+    all_feats.rows += feats.rows;
+  }
+  fclose(f);
+  // The reference runs no CMVN between fbank and AM (src/ce_stt.cc:307-331); with stats given the
+  // test inserts it, whole utterance then frame by frame in order.
+  Matrix norm = all_feats;
+  if (!stats.empty()) {
+    CMVN cmvn(stats, all_feats, 0);
+    for (int t = 0; t < all_feats.rows; ++t) {
+      st = cmvn.GetFrame(t, norm.Row(t));
+      if (!st.ok()) return Fail("CMVN::GetFrame", st);
+    }
+  }
+  int batches = 0;
+  for (int t = 0; t < norm.rows; ++t) {
+    Matrix lp;
+    st = am.Process(&am_inst, norm.Row(t), &lp);
+    if (!st.ok()) return Fail("AcousticModel::Process", st);
+    if (lp.NumRows()) ++batches;
+    rows.insert(rows.end(), lp.data.begin(), lp.data.end());
+  }
+  Matrix lp;
+  st = am.EndOfStream(&am_inst, &lp);
+  if (!st.ok()) return Fail("AcousticModel::EndOfStream", st);
+  rows.insert(rows.end(), lp.data.begin(), lp.data.end());
+  const int32_t hdr[3] = {(int32_t)(rows.size() / am.num_pdfs()), am.num_pdfs(), batches};
+  FILE *o = fopen(out_path.c_str(), "wb");
+  if (!o) return Fail("open out", Status::IOError(out_path));
+  fwrite(hdr, 4, 3, o);
+  fwrite(rows.data(), 4, rows.size(), o);
+  fclose(o);
+  printf("OK rows=%d cols=%d batches=%d tid2pdf=%zu\n", hdr[0], hdr[1], batches, am.TransitionPdfIdMap().size());
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc >= 2 && strcmp(argv[1], "errors") == 0) return Errors();
+  if (argc >= 6 && strcmp(argv[1], "stream") == 0) return Stream(argc, argv);
+  fprintf(stderr, "usage: %s errors | stream <conf> <pcm> <out> <precision> [cmvn_stats]\n", argv[0]);
+  return 2;
+}

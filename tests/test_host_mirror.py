@@ -1,0 +1,91 @@
+"""include/ce_host.hpp: the C++ host side that mirrors the reference's operator surface
+(Fbank::Process, CMVN::GetFrame, AcousticModel::Read/Process/EndOfStream) over the C ABI.
+The test program (tests/cpp/host_mirror_test.cc) drives it like src/ce_stt.cc drives the
+reference: 1 KB PCM pieces, one frame at a time into the AM, rows collected for the decoder."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from catears_b200 import api, formats as F, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    if not os.path.exists(api.LIB_PATH):
+        pytest.fail("libce_gpu.so is missing: run `make lib`")
+    out = str(tmp_path_factory.mktemp("host_mirror") / "host_mirror_test")
+    libdir = os.path.dirname(api.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cc"), "-o", out,
+                           "-L" + libdir, "-lce_gpu", "-Wl,-rpath," + libdir])
+    return out
+
+
+def test_host_mirror_error_behaviour(exe):
+    """Missing files, calls before Read, non-int16 samples and (here, without a GPU) the absence
+    of any CPU fallback all come back as a Status with a message."""
+    r = subprocess.run([exe, "errors"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "OK"
+
+
+def _stream(exe, tmp_path, model, pcm, precision, stats_path=None):
+    pcm_path = str(tmp_path / "utt.s16le")
+    out_path = str(tmp_path / ("out_%d.bin" % precision))
+    pcm.astype("<i2").tofile(pcm_path)
+    cmd = [exe, "stream", model["conf"], pcm_path, out_path, str(precision)]
+    if stats_path:
+        cmd.append(stats_path)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.int32, 3)
+    rows, cols, batches = int(raw[0]), int(raw[1]), int(raw[2])
+    data = np.fromfile(out_path, np.float32, offset=12).reshape(rows, cols)
+    return data, batches
+
+
+@pytest.mark.gpu
+def test_host_mirror_streaming_equals_batch_and_oracle(exe, tmp_path, golden, port):
+    """chunk_size 16 forces many Process() batches; the concatenated rows must equal the whole-
+    utterance evaluation (chunked == whole) and the oracle's float path (1e-3)."""
+    stats = golden["cmvn_stats"]
+    m = synth.write_model(str(tmp_path / "m"), name="small", hidden=64, num_pdfs=96, seed=4321,
+                          chunk_size=16)
+    stats_path = str(tmp_path / "stats.vec0")
+    F.write_vector(stats_path, stats)
+    pcm = golden["hello_pcm"]
+    got, batches = _stream(exe, tmp_path, m, pcm, api.PRECISION_FP32, stats_path)
+    assert got.shape == (47, 96) and batches == 2            # 47 frames = 2 x 16 + 15 at end of stream
+    feats = port.cmvn(stats, port.fbank(pcm))
+    prior = F.read_vector(m["prior"])
+    want = port.am_forward(m["nnet"], prior, m["left"], m["right"], feats, mode="float")
+    assert np.abs(got - want).max() < 1e-3
+    am = api.AcousticModelGpu(config=m["conf"], precision="fp32")
+    whole, _ = am.nnet(api.cmvn(stats, api.fbank(pcm)))
+    am.close()
+    assert np.abs(got - whole).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_host_mirror_int8_matches_batch_api(exe, tmp_path, golden):
+    """int8 through the mirror: with chunk_size > T the buffered frames (which carry the reference's
+    explicit edge replication, src/am.cc:119-124,152-155) are evaluated as ONE matrix; the rows must
+    be bit-identical to the batch API fed the same explicitly padded matrix."""
+    m = synth.write_model(str(tmp_path / "m8"), name="small", hidden=64, num_pdfs=96, seed=4321)
+    pcm = golden["hello_pcm"]
+    got, batches = _stream(exe, tmp_path, m, pcm, api.PRECISION_INT8)
+    assert got.shape == (47, 96) and batches == 0
+    feats = api.fbank(pcm)
+    L, R = m["left"], m["right"]
+    padded = np.concatenate([np.repeat(feats[:1], L, 0), feats, np.repeat(feats[-1:], R, 0)])
+    am = api.AcousticModelGpu(config=m["conf"], precision="int8")
+    whole, _ = am.nnet(padded)
+    am.close()
+    assert np.array_equal(got, whole[L:L + 47])
