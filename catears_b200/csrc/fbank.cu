@@ -41,6 +41,9 @@ constexpr int kChunkSamples = (kChunkFrames - 1) * kFrameShift + kFrameLen;   //
 constexpr int kXsLen = kChunkSamples + 16;             // + alignment slack
 constexpr int kBlocksPerChunk = kChunkSamples / 80;    // 67 blocks of 80 samples
 constexpr int kXchgStride = 17;                        // padded 16x16 float2 transpose
+// float2 per half-warp buffer: 16 x 17 + 8, i.e. 560 floats == 16 (mod 32), so the two half-warps of
+// a warp (which run the same instruction on their own buffers) land on disjoint shared-memory banks
+constexpr int kXchgBuf = 16 * kXchgStride + 8;
 constexpr int kMaxSlots = kMaxMel / 16;
 
 struct ChunkDesc {        // one per CTA
@@ -63,14 +66,32 @@ struct FbankTablesDev {   // lives in global memory, copied to smem by every CTA
   int32_t slot_iters[kMaxSlots];
   int32_t n_slots;
   int32_t n_weights;
-  float weights[1];       // n_weights floats, each 0.25 * reference weight
+  float weights[1];       // n_weights floats, each 0.25 * reference weight; slot-major, then
+                          // [iteration][lane] so that a half-warp reads 16 consecutive floats
 };
 
 // ---------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add / subtract as ONE packed fp32x2 instruction (sm_100 add.f32x2 / sub.f32x2): the FFT's
+// butterflies are mostly these, so the packed forms halve its issue slots; each half is an ordinary
+// IEEE round-to-nearest fp32 operation.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -80,8 +101,9 @@ __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 
   float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
   a0 = cadd(t0, t2);
   a2 = csub(t0, t2);
-  a1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i t3
-  a3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i t3
+  const float2 r3 = make_float2(t3.y, -t3.x);   // -i t3
+  a1 = cadd(t1, r3);                             // t1 - i t3
+  a3 = csub(t1, r3);                             // t1 + i t3
 }
 
 // a * exp(-2 pi i M / 16)
@@ -116,13 +138,14 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 //   in : lane n1 holds z[n1 + 16 n2] in v[n2]
 //   out: lane k2 holds Z[k2 + 16 k1] in v[FFT16_POS(k1)]
 // tw[k2] = exp(-2 pi i n1 k2 / 256) for this lane; xchg = this half-warp's 16x17 float2 buffer.
-__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], const float2 (&tw)[16],
+template <int TW_STRIDE>
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], const float2 *tw,
                                                 float2 *xchg, int t) {
   fft16(v);
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) {
     float2 y = v[FFT16_POS(k2)];
-    if (k2 > 0) y = cmul(y, tw[k2]);
+    if (k2 > 0) y = cmul(y, tw[k2 * TW_STRIDE]);
     xchg[k2 * kXchgStride + t] = y;
   }
   __syncwarp();
@@ -182,23 +205,25 @@ __device__ __forceinline__ void rfft_power(const float2 (&v)[16], float2 wt, flo
 // ---------------------------------------------------------------------------
 struct SmemLayout {
   // byte offsets into dynamic shared memory
-  int xs, d, bsum, xchg, hamming, weights, total;
+  int xs, d, bsum, x0, xchg, hamming, weights, tw, total;
 };
 
 __host__ __device__ inline SmemLayout MakeLayout(int n_weights) {
   SmemLayout L;
   int o = 0;
   L.d = o;        o += kXsLen * 4;                         // float d[]
-  L.xchg = o;     o += kHalfWarps * 16 * kXchgStride * 8;  // float2 per half-warp
+  L.xchg = o;     o += kHalfWarps * kXchgBuf * 8;          // float2 per half-warp (phase 2)
+  L.xs = L.xchg;                                           // int16 xs[] (phase 1 only): same bytes
   L.hamming = o;  o += kFrameLen * 4;
   L.weights = o;  o += ((n_weights + 3) & ~3) * 4;
+  L.tw = o;       o += 256 * 8;                            // float2 tw[k2][t] (lane-contiguous)
   L.bsum = o;     o += ((kBlocksPerChunk + 1 + 3) & ~3) * 4;
-  L.xs = o;       o += kXsLen * 2;                         // int16 xs[]
+  L.x0 = o;       o += kChunkFrames * 4;                   // first sample of every frame
   L.total = (o + 15) & ~15;
   return L;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
              const ChunkDesc *__restrict__ chunks, const FbankTablesDev *__restrict__ tab,
              int num_mel, float *__restrict__ out, int64_t out_stride) {
@@ -208,8 +233,10 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
   float2 *xchg_all = reinterpret_cast<float2 *>(smem + L.xchg);
   float *s_ham = reinterpret_cast<float *>(smem + L.hamming);
   float *s_w = reinterpret_cast<float *>(smem + L.weights);
+  float2 *s_tw = reinterpret_cast<float2 *>(smem + L.tw);
   int *bsum = reinterpret_cast<int *>(smem + L.bsum);
   int16_t *xs = reinterpret_cast<int16_t *>(smem + L.xs);
+  float *x0s = reinterpret_cast<float *>(smem + L.x0);
 
   const ChunkDesc cd = chunks[blockIdx.x];
   const int tid = threadIdx.x;
@@ -231,6 +258,7 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
   }
   for (int i = tid; i < kFrameLen; i += kThreads) s_ham[i] = tab->hamming[i];
   for (int i = tid; i < tab->n_weights; i += kThreads) s_w[i] = tab->weights[i];
+  for (int i = tid; i < 256; i += kThreads) s_tw[(i & 15) * 16 + (i >> 4)] = tab->tw256[i];   // [n1][k2] -> [k2][n1]
   __syncthreads();
 
   // ---- phase 1b: d[s] = x[s] - 0.97 x[s-1]; exact sums of 80-sample blocks ----
@@ -247,19 +275,18 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
       for (int j = 0; j < 80; ++j) s += x[80 * b + j];
       bsum[b] = s;
     }
+    for (int f = tid; f < cd.n_frames; f += kThreads) x0s[f] = (float)x[f * kFrameShift];
   }
-  __syncthreads();
+  __syncthreads();                                         // xs is dead from here: xchg reuses its bytes
 
   // ---- phase 2: one frame per half-warp ----
   const int lane = tid & 31;
   const int t = tid & 15;
   const int hw = tid >> 4;
-  float2 *xchg = xchg_all + hw * 16 * kXchgStride;
+  float2 *xchg = xchg_all + hw * kXchgBuf;
   float *p4 = reinterpret_cast<float *>(xchg);             // reused after the transpose
 
-  float2 tw[16];
-#pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) tw[k2] = tab->tw256[t * 16 + k2];
+  const float2 *tw = s_tw + t;                             // tw[16 k2] = exp(-2 pi i t k2 / 256)
   const float2 wt = tab->tw512[t];
   const int n_slots = tab->n_slots;
 
@@ -289,11 +316,11 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
       }
     }
     if (t == 0) {                                          // sample 0: y0 - 0.97 y0 (fbank.cc:61)
-      float y0 = (float)x[fs] - mean;
+      float y0 = x0s[live ? f : 0] - mean;
       v[0].x = fmaf(-0.97f, y0, y0) * s_ham[0];
     }
 
-    fft256_halfwarp(v, tw, xchg, t);
+    fft256_halfwarp<16>(v, tw, xchg, t);
     rfft_power(v, wt, p4, t, lane);
     __syncwarp();
 
@@ -304,7 +331,7 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
       const int iters = tab->slot_iters[s];
       float acc = 0.0f;
       for (int i = 0; i < iters; ++i) {
-        if (i < ms.width) acc = fmaf(s_w[ms.woff + i], p4[ms.k0 + i], acc);
+        if (i < ms.width) acc = fmaf(s_w[ms.woff + 16 * i], p4[ms.k0 + i], acc);
       }
       if (live && ms.mel >= 0) orow[ms.mel] = logf(fmaxf(acc, FLT_EPSILON));
     }
@@ -332,7 +359,7 @@ rfft512_kernel(const float *__restrict__ in, int n_frames, const FbankTablesDev 
     float2 v[16];
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = *reinterpret_cast<const float2 *>(row + 2 * t + 32 * n2);
-    fft256_halfwarp(v, tw, xchg, t);
+    fft256_halfwarp<1>(v, tw, xchg, t);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) zbuf[t + 16 * k1] = v[FFT16_POS(k1)];
     __syncwarp();
@@ -376,8 +403,8 @@ int BuildTables(int num_mel, HostTables *ht) {
   const float bin_width = sample_freq / kFftSize;
   const float mel_low = MelScale(20), mel_high = MelScale(8000);
   const float delta = (mel_high - mel_low) / (num_mel + 1);
-  std::vector<int> off(num_mel), width(num_mel), woff(num_mel);
-  std::vector<float> weights;
+  std::vector<int> off(num_mel), width(num_mel);
+  std::vector<std::vector<float>> fw(num_mel);
   for (int b = 0; b < num_mel; ++b) {
     float left = mel_low + b * delta;
     float center = mel_low + (b + 1) * delta;
@@ -398,10 +425,41 @@ int BuildTables(int num_mel, HostTables *ht) {
     }
     off[b] = first;
     width[b] = last + 1 - first;
-    woff[b] = (int)weights.size();
-    for (int i = first; i <= last; ++i) weights.push_back(0.25f * tmp[i]);   // exact scaling
+    for (int i = first; i <= last; ++i) fw[b].push_back(0.25f * tmp[i]);   // exact scaling
   }
-  ht->n_weights = (int)weights.size();
+
+  // Slots: 16 filters per slot, one per lane.  Filters are placed widest first into the earliest
+  // slot with a free lane in which no filter has the same first bin modulo 16: lane t reads
+  // p4[k0_t + i] in iteration i, so distinct k0 mod 16 means distinct banks for the whole warp
+  // (the other half-warp's buffer is 16 banks away).
+  const int n_slots = (num_mel + 15) / 16;
+  std::vector<std::vector<int>> members(n_slots);
+  {
+    std::vector<int> order(num_mel);
+    for (int b = 0; b < num_mel; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return width[a] > width[b]; });
+    for (int b : order) {
+      int pick = -1;
+      for (int s2 = 0; s2 < n_slots && pick < 0; ++s2) {
+        if ((int)members[s2].size() >= 16) continue;
+        bool clash = false;
+        for (int o2 : members[s2]) clash = clash || (off[o2] % 16 == off[b] % 16);
+        if (!clash) pick = s2;
+      }
+      for (int s2 = 0; s2 < n_slots && pick < 0; ++s2)
+        if ((int)members[s2].size() < 16) pick = s2;       // no clash-free slot left: accept a conflict
+      members[pick].push_back(b);
+    }
+  }
+  int total_w = 0;
+  std::vector<int> slot_iters(kMaxSlots, 0), slot_off(kMaxSlots, 0);
+  for (int s2 = 0; s2 < n_slots; ++s2) {
+    for (int b : members[s2]) slot_iters[s2] = std::max(slot_iters[s2], width[b]);
+    slot_off[s2] = total_w;
+    total_w += 16 * slot_iters[s2];
+  }
+  std::vector<float> weights((size_t)total_w, 0.0f);
+  ht->n_weights = total_w;
   size_t bytes = sizeof(FbankTablesDev) + sizeof(float) * weights.size();
   ht->blob.assign(bytes, 0);
   FbankTablesDev *T = reinterpret_cast<FbankTablesDev *>(ht->blob.data());
@@ -423,25 +481,20 @@ int BuildTables(int num_mel, HostTables *ht) {
     double ang = -2.0 * kPi * (double)t / 512.0;
     T->tw512[t] = make_float2((float)cos(ang), (float)sin(ang));
   }
-  // Slots: filters sorted by width (descending), 16 per slot, one per lane.
-  std::vector<int> order(num_mel);
-  for (int b = 0; b < num_mel; ++b) order[b] = b;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return width[a] > width[b]; });
-  T->n_slots = (num_mel + 15) / 16;
-  for (int s = 0; s < kMaxSlots; ++s) {
-    T->slot_iters[s] = 0;
+  T->n_slots = n_slots;
+  for (int s2 = 0; s2 < kMaxSlots; ++s2) {
+    T->slot_iters[s2] = slot_iters[s2];
     for (int t = 0; t < 16; ++t) {
       MelSlot ms = {0, 0, -1, 0, 0};
-      int idx = s * 16 + t;
-      if (idx < num_mel) {
-        int b = order[idx];
+      if (s2 < n_slots && t < (int)members[s2].size()) {
+        const int b = members[s2][t];
         ms.k0 = (int16_t)off[b];
         ms.width = (int16_t)width[b];
         ms.mel = (int16_t)b;
-        ms.woff = woff[b];
-        T->slot_iters[s] = std::max(T->slot_iters[s], width[b]);
+        ms.woff = slot_off[s2] + t;
+        for (int i = 0; i < width[b]; ++i) weights[(size_t)slot_off[s2] + 16 * i + t] = fw[b][i];
       }
-      T->slots[s][t] = ms;
+      T->slots[s2][t] = ms;
     }
   }
   T->n_weights = ht->n_weights;
