@@ -269,11 +269,14 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
     d[i] = fmaf(-0.97f, prev, cur);
   }
   {
+    // one warp per 80-sample block: consecutive lanes read consecutive samples (no bank conflicts)
     const int n_blocks = n_samples / 80;
-    for (int b = tid; b < n_blocks; b += kThreads) {
-      int s = 0;
-      for (int j = 0; j < 80; ++j) s += x[80 * b + j];
-      bsum[b] = s;
+    for (int b = tid >> 5; b < n_blocks; b += kThreads / 32) {
+      const int j = tid & 31;
+      int s = x[80 * b + j] + x[80 * b + 32 + j] + (j < 16 ? x[80 * b + 64 + j] : 0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (j == 0) bsum[b] = s;
     }
     for (int f = tid; f < cd.n_frames; f += kThreads) x0s[f] = (float)x[f * kFrameShift];
   }
