@@ -420,6 +420,91 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_frontend(args):
+    """fbank + CMVN only, 10,000 synthetic 10 s utterances (256 distinct ones
+    tiled), 40 or 80 mel bins.  One JSON line with the fbank kernel's HBM roofline."""
+    import torch
+    from catears_b200 import api, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    n_utts = args.frontend_utts // world
+    mel = args.mel
+    base, _ = synth.synth_batch(min(256, n_utts), 160000, first=rank * 256)
+    pcm_np = np.tile(base, (n_utts + 255) // 256)[:n_utts * 160000]
+    off = np.arange(n_utts + 1, dtype=np.int64) * 160000
+    foff = api.frame_offsets(off)
+    frames = int(foff[-1])
+    stats = synth.default_cmvn_stats(mel=mel)
+    h_pcm = torch.from_numpy(pcm_np).pin_memory()
+    d_pcm = h_pcm.cuda()
+    d_fb = torch.empty((frames, mel), dtype=torch.float32, device="cuda")
+    d_out = torch.empty_like(d_fb)
+    h_out = torch.empty((frames, mel), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        api.fbank(d_pcm, off, num_mel=mel, out=d_fb, device=local_rank, stream=stream)
+        api.cmvn(stats, d_fb, foff, out=d_out, device=local_rank, stream=stream)
+
+    def step_e2e():
+        api.fbank(h_pcm.numpy(), off, num_mel=mel, out=d_fb, device=local_rank, stream=stream)
+        api.cmvn(stats, d_fb, foff, out=h_out.numpy(), device=local_rank, stream=stream)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(args.warmup):
+        step_device()
+    api.launch_count(reset=True)
+    ms = timed(step_device, args.steps)
+    launches = api.launch_count()
+    api.profile_enable(True)
+    timed(step_device, args.steps)
+    prof = api.profile_read()
+    api.profile_enable(False)
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(1, args.steps // 2)) / max(1, args.steps // 2) * args.steps
+    if rank != 0:
+        return
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    audio = world * n_utts * UTT_SECONDS * args.steps
+    fb_ms, fb_n = prof["fbank"]
+    bytes_per_frame = 320 + 4 * mel
+    gbs = frames * bytes_per_frame * args.steps / (fb_ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "audio-sec/sec (RTFx) fbank+CMVN", "value": round(audio / (ms * 1e-3), 1), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 2: fbank+CMVN only, %d synthetic 10 s 16 kHz utterances per GPU "
+                               "(256 distinct, tiled), %d mel bins" % (n_utts, mel),
+                   "frames_per_step": frames * world,
+                   "l2": "inputs larger than L2 (%.1f GB PCM per GPU per step)" % (pcm_np.nbytes / 1e9)},
+        "e2e": {"value": round(audio / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                "h2d_bytes_per_step": int(pcm_np.nbytes) * world,
+                "d2h_bytes_per_step": int(frames * mel * 4) * world},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "fbank_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak,
+                     "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "traffic": None,
+                     "algorithmic_bytes_per_launch": frames * bytes_per_frame,
+                     "avg_launch_ms": round(fb_ms / max(1, fb_n), 4),
+                     "note": "fp32-issue and shared-memory bound, not HBM bound: see DESIGN.md section 5"},
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,10 +515,16 @@ def main():
     ap.add_argument("--utts-per-gpu", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-loglik", action="store_true")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "frontend"],
+                    help="pipeline = the headline fbank+CMVN+AM step (default); frontend = config 2")
+    ap.add_argument("--frontend-utts", type=int, default=10000)
+    ap.add_argument("--mel", type=int, default=40)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = max(args.warmup, 1)
-    if args.impl == "reference":
+    if args.workload == "frontend" and args.impl == "native":
+        run_frontend(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: plain `python bench.py --gpus N` re-launches itself under torchrun
