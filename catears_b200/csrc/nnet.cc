@@ -38,6 +38,7 @@ ce_gpu_model::~ce_gpu_model() {
   }
   log_prior.Free(); cmvn_dev.Free();
   stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
+  stage_argmax_all.Free();
   ws[0].Free(); ws[1].Free();
   if (inputs_ready) cudaEventDestroy(inputs_ready);
   if (call_start) cudaEventDestroy(call_start);
@@ -463,6 +464,10 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     CE_CUDA(cudaEventRecord(m->call_start, s));          // already queued on s has run
     CE_CUDA(cudaStreamWaitEvent(m->copy_stream, m->call_start, 0));
   }
+  // The per-frame argmax is 4 bytes a frame: it is staged for the whole batch and copied out once,
+  // so that no device-to-host copy sits between two chunks on the compute stream.
+  const int64_t total_frames = frame_off[n_utts] - frame_off[0];
+  if (am_host) CE_CHECK(m->stage_argmax_all.Reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total_frames, 1)));
   bool used[2] = {false, false};
   int u0 = 0, chunk = 0;
   while (u0 < n_utts) {
@@ -492,10 +497,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CHECK(w->stage_loglik.Reserve(sizeof(float) * (size_t)nf * NP));
       ll_dev = w->stage_loglik.as<float>() - f0 * NP;     // row f0 lands on the staging buffer's row 0
     }
-    if (am_host) {
-      CE_CHECK(w->stage_argmax.Reserve(sizeof(int32_t) * (size_t)nf));
-      am_dev = w->stage_argmax.as<int32_t>() - f0;
-    }
+    if (am_host) am_dev = m->stage_argmax_all.as<int32_t>() - frame_off[0];   // whole batch, one copy at the end
     PcmSource src = all;
     if (all.pcm_dev) src.sample_off = all.sample_off + u0;
     if (all.pcm_host && all.sample_off[u1] > all.sample_off[u0]) {
@@ -515,10 +517,6 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, w->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
                               cudaMemcpyDeviceToHost, cs));
     }
-    if (am_host && nf > 0) {
-      CE_CUDA(cudaMemcpyAsync(argmax + f0, w->stage_argmax.ptr, sizeof(int32_t) * (size_t)nf,
-                              cudaMemcpyDeviceToHost, cs));
-    }
     u0 = u1;
     ++chunk;
   }
@@ -528,6 +526,10 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CUDA(cudaEventRecord(m->ws[i].done, m->ws[i].stream));
       CE_CUDA(cudaStreamWaitEvent(s, m->ws[i].done, 0));
     }
+  }
+  if (am_host && total_frames > 0) {
+    CE_CUDA(cudaMemcpyAsync(argmax + frame_off[0], m->stage_argmax_all.ptr, sizeof(int32_t) * (size_t)total_frames,
+                            cudaMemcpyDeviceToHost, s));
   }
   if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));   // host outputs are complete on return
   return CE_GPU_OK;

@@ -43,7 +43,7 @@ struct ce_gpu_model {
   int64_t max_chunk_rows = 131072;
 
   // ---- workspace (one forward call at a time per handle) ----
-  ce::DevBuf stage_pcm, stage_feats;
+  ce::DevBuf stage_pcm, stage_feats, stage_argmax_all;
   ce::DevBuf feats;                    // fbank output / staged features [frames x feat_dim]
   ce::Table fbank_chunks;
   // Chunks of utterances alternate between two workspaces on two internal streams, so that the

@@ -32,17 +32,23 @@ def main():
     conf = os.path.join(bench.model_dir(), "tdnn.conf")
     pcm, off = synth.synth_batch(n_utts, 160000)
     model = api.AcousticModelGpu(config=conf, precision="int8")
-    d_pcm = torch.from_numpy(pcm).cuda()
+    host = os.environ.get("TRACE_HOST_PCM") == "1"     # e2e flavour: pinned host PCM in, host argmax out
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    d_pcm = h_pcm.numpy() if host else h_pcm.cuda()
     frames = int(api.frame_offsets(off)[-1])
     d_ll = torch.empty((frames, model.num_pdfs), dtype=torch.float32, device="cuda")
-    d_am = torch.empty(frames, dtype=torch.int32, device="cuda")
+    d_am = torch.empty(frames, dtype=torch.int32).pin_memory().numpy() if host else \
+        torch.empty(frames, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream()
     for _ in range(3):
         model.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=s)
     torch.cuda.synchronize()
     api.profile_enable(True)
+    import time
+    t0 = time.perf_counter()
     model.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=s)
     torch.cuda.synchronize()
+    print("host wall time of the call: %.3f ms" % (1e3 * (time.perf_counter() - t0)))
     tr = api.profile_trace()
     api.profile_enable(False)
     t_end = max(t[2] for t in tr)
