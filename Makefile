@@ -35,7 +35,7 @@ $(LIB): $(OBJS)
 
 oracle:
 	$(MAKE) -C oracle port
-	@if [ -d /root/reference/src ]; then $(MAKE) -C oracle ref ref-sse4; else echo "reference absent: keeping prebuilt oracle/_ref"; fi
+	@if [ -d /root/reference/src ]; then $(MAKE) -C oracle ref ref-sse4 && $(MAKE) lib && $(MAKE) -C oracle dropin; else echo "reference absent: keeping prebuilt oracle/_ref"; fi
 
 clean:
 	rm -rf $(BUILD) $(LIB)

@@ -1,0 +1,120 @@
+"""SURVEY 8f rank 1 -- the drop-in itself: the reference's own `pocketkaldi` binary built twice from
+the reference sources where they lie (oracle/Makefile `dropin`):
+
+  oracle/_ref/pocketkaldi_ref   every reference source unchanged (CPU fbank + AM + decoder)
+  oracle/_ref/pocketkaldi_gpu   the same sources, except that src/ce_stt.cc is replaced by
+                                integration/ce_stt_gpu.cc (front end + AM through libce_gpu.so);
+                                decoder, FST, hash table, symbol table and WAV reader are the
+                                reference's unchanged code, its CPU fbank is not linked and its
+                                cblas_sgemm aborts if reached.
+
+Both decode the same audio with the same synthetic model and graph (the reference bundles neither,
+SURVEY D5); the recognised word sequences must be identical."""
+import os
+import subprocess
+import wave
+
+import numpy as np
+import pytest
+
+from catears_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+BIN_REF = os.path.join(REF_DIR, "pocketkaldi_ref")
+BIN_GPU = os.path.join(REF_DIR, "pocketkaldi_gpu")
+MAKE_GRAPH = os.path.join(REF_DIR, "make_graph")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.skipif(
+    not all(os.path.exists(p) for p in (BIN_REF, BIN_GPU, MAKE_GRAPH)),
+    reason="oracle/_ref drop-in binaries were never built (needs /root/reference: make -C oracle dropin)")
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("dropin"))
+    m = input_sensitive_model(d)
+    subprocess.check_call([MAKE_GRAPH, d, "96", "12", "7"], stdout=subprocess.DEVNULL)
+    os.replace(os.path.join(d, "tid2pdf.bin"), m["tid2pdf"])      # the graph's transition-id map
+    with open(m["conf"], "a") as f:
+        f.write("fst = HCLG.fst\nsymbol_table = words.txt\n")
+    wav = os.path.join(d, "synth10s.wav")
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        # 10 s of a gated frequency sweep: a non-stationary spectrum, so that the best path really
+        # moves through the graph (stationary noise keeps the decoder on one word)
+        rng = np.random.default_rng(5)
+        t = np.arange(160000) / 16000.0
+        f = 300 + 3000 * (0.5 + 0.5 * np.sin(2 * np.pi * 0.7 * t))
+        ph = 2 * np.pi * np.cumsum(f) / 16000.0
+        pcm = 6000 * np.sin(ph) * (0.3 + 0.7 * (np.sin(2 * np.pi * 3 * t) > 0)) + 50 * rng.standard_normal(t.size)
+        w.writeframes(np.clip(np.round(pcm), -32768, 32767).astype("<i2").tobytes())
+    scp = os.path.join(d, "list.scp")
+    with open(scp, "w") as f:
+        f.write("hello %s\ncat %s\nsynth %s\n" % (os.path.join(GOLDEN, "en-us-hello.wav"),
+                                                 os.path.join(GOLDEN, "en-us-cat.wav"), wav))
+    return {"conf": m["conf"], "wav": wav, "scp": scp}
+
+
+def input_sensitive_model(d, num_pdfs=96, hidden=64, seed=99):
+    """A two-layer TDNN whose output really depends on the audio (a random deep stack on raw,
+    un-normalised fbank gives almost the same distribution for every frame, and the decoder would
+    then stay on one word): the first layer's bias removes the features' common offset, the last
+    layer has a gain, the prior is flat.  Written in the reference's NN02 / VEC0 / config formats."""
+    from catears_b200 import formats as F
+    rng = np.random.default_rng(seed)
+    k = 3 * 40
+    w1 = (rng.standard_normal((k, hidden)) / np.sqrt(k)).astype(np.float32)
+    b1 = (-14.0 * w1.sum(0)).astype(np.float32)
+    w2 = (3.0 * rng.standard_normal((hidden, num_pdfs)) / np.sqrt(hidden)).astype(np.float32)
+    layers = [{"type": F.SPLICE, "indices": [-1, 0, 1]}, {"type": F.NARROW, "left": 1, "right": 1},
+              {"type": F.LINEAR, "W": w1, "b": b1}, {"type": F.RELU},
+              {"type": F.BATCHNORM, "scale": rng.uniform(0.5, 1.5, hidden).astype(np.float32),
+               "offset": (0.1 * rng.standard_normal(hidden)).astype(np.float32)},
+              {"type": F.LINEAR, "W": w2, "b": np.zeros(num_pdfs, np.float32)}, {"type": F.LOGSOFTMAX}]
+    p = {x: os.path.join(d, "toy." + x) for x in ("nnet", "prior", "tid2pdf", "conf")}
+    F.write_nnet(p["nnet"], layers, 1, 1)
+    F.write_vector(p["prior"], np.full(num_pdfs, 1.0 / num_pdfs, np.float32))
+    F.write_vector(p["tid2pdf"], np.arange(num_pdfs, dtype=np.int32), dtype="<i4")
+    F.write_am_config(p["conf"], p["nnet"], p["prior"], 1, 1, 16, num_pdfs, p["tid2pdf"], {})
+    return p
+
+
+def run(binary, conf, audio, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([binary, conf, audio], capture_output=True, text=True, env=e)
+
+
+def test_reference_binary_decodes_with_synthetic_graph(setup):
+    """The unmodified reference (CPU) runs end to end on the synthetic model + graph."""
+    r = run(BIN_REF, setup["conf"], os.path.join(GOLDEN, "en-us-hello.wav"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().startswith("word")
+
+
+def test_gpu_binary_has_no_cpu_fallback(setup):
+    if api.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    r = run(BIN_GPU, setup["conf"], os.path.join(GOLDEN, "en-us-hello.wav"))
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_unchanged_decoder_on_gpu_loglikelihoods_matches_reference(setup):
+    """Same words from the reference's CPU pipeline and from its unchanged decoder fed by the GPU
+    front end + acoustic model: single wavs, a 10 s utterance, and an .scp list."""
+    for audio in (os.path.join(GOLDEN, "en-us-hello.wav"), os.path.join(GOLDEN, "en-us-cat.wav"),
+                  setup["wav"], setup["scp"]):
+        ref = run(BIN_REF, setup["conf"], audio)
+        gpu = run(BIN_GPU, setup["conf"], audio)
+        assert ref.returncode == 0, ref.stdout + ref.stderr
+        assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert ref.stdout.strip() != ""
+        assert gpu.stdout == ref.stdout, (audio, ref.stdout, gpu.stdout)
+    words = run(BIN_REF, setup["conf"], setup["wav"]).stdout.split()
+    assert len(words) >= 20 and len(set(words)) >= 3              # a real path through the graph
