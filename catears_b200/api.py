@@ -25,7 +25,7 @@ EXPORTS = [
     "ce_gpu_fbank", "ce_gpu_cmvn", "ce_gpu_rfft512", "ce_gpu_nnet", "ce_gpu_forward",
     "ce_gpu_nnet_keep_acc", "ce_gpu_nnet_get_acc", "ce_gpu_quantize", "ce_gpu_gemm_u8",
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
-    "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer",
+    "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer", "ce_gpu_cmvn_stream",
     "ce_gpu_partition", "ce_gpu_time_shards",
 ]
 PROFILE_CATEGORIES = ["fbank", "cmvn", "gemm", "quantize", "finalize", "other"]
@@ -59,6 +59,8 @@ def lib():
     L.ce_gpu_frame_offsets.argtypes = [i64p, C.c_int, i64p]
     L.ce_gpu_fbank.argtypes = [vp, i64p, C.c_int, C.c_int, vp, C.c_int, vp]
     L.ce_gpu_cmvn.argtypes = [vp, vp, i64p, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.ce_gpu_cmvn_stream.argtypes = [vp, vp, i64p, C.POINTER(C.c_int32), i64p, vp, C.c_int, C.c_int, vp,
+                                     C.c_int, vp]
     L.ce_gpu_rfft512.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     L.ce_gpu_nnet.argtypes = [vp, vp, i64p, C.c_int, vp, vp, vp]
     L.ce_gpu_forward.argtypes = [vp, vp, i64p, C.c_int, vp, vp, i64p, vp]
@@ -205,6 +207,23 @@ def cmvn(global_stats, feats, frame_offsets_=None, out=None, device=0, stream=No
         out = np.zeros((int(off[-1]), num_mel), np.float32)
     _check(lib().ce_gpu_cmvn(g.ctypes.data, _ptr(feats), p, off.size - 1, num_mel, _ptr(out), device,
                              _stream(stream)), "ce_gpu_cmvn")
+    return out
+
+
+def cmvn_stream(global_stats, feats, frame_offsets_, n_hist, t_base, state, device=0):
+    """CMVN continued across calls: see ce_gpu_cmvn_stream.  `state` ([n x mel] float32) is updated in
+    place; returns the normalised NEW frames, packed by utterance."""
+    g = np.ascontiguousarray(global_stats, np.float32)
+    num_mel = g.size - 1
+    off, p = _offsets(frame_offsets_)
+    nh = np.ascontiguousarray(n_hist, np.int32)
+    tb, ptb = _offsets(t_base)
+    assert state.dtype == np.float32 and state.flags["C_CONTIGUOUS"]
+    n_new = int((off[1:] - off[:-1]).sum() - nh.sum())
+    out = np.zeros((n_new, num_mel), np.float32)
+    _check(lib().ce_gpu_cmvn_stream(g.ctypes.data, _ptr(feats), p, nh.ctypes.data_as(C.POINTER(C.c_int32)), ptb,
+                                    state.ctypes.data, off.size - 1, num_mel, _ptr(out), device, None),
+           "ce_gpu_cmvn_stream")
     return out
 
 

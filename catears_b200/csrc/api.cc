@@ -266,6 +266,55 @@ int ce_gpu_cmvn(const float *global_stats, const float *feats, const int64_t *ut
   return Deliver(out, out_dev, bytes, s);
 }
 
+int ce_gpu_cmvn_stream(const float *global_stats, const float *feats, const int64_t *utt_frame_offsets,
+                       const int32_t *n_hist, const int64_t *t_base, float *state, int n_utts,
+                       int num_mel, float *out, int device, void *stream) {
+  CE_CHECK(CheckOffsets(utt_frame_offsets, n_utts, "ce_gpu_cmvn_stream"));
+  if (n_utts == 0) return CE_GPU_OK;
+  if (!global_stats || !feats || !out || !n_hist || !t_base || !state || num_mel < 1) {
+    SetError("ce_gpu_cmvn_stream: null buffer / bad num_mel");
+    return CE_GPU_EINVAL;
+  }
+  std::vector<int64_t> out_off(n_utts + 1, 0);
+  for (int u = 0; u < n_utts; ++u) {
+    const int64_t rows = utt_frame_offsets[u + 1] - utt_frame_offsets[u];
+    if (n_hist[u] < 0 || n_hist[u] > rows || t_base[u] < n_hist[u] ||
+        n_hist[u] != std::min<int64_t>(t_base[u], kCmvnWindow)) {
+      SetError("ce_gpu_cmvn_stream: utterance %d must bring min(t_base, %d) history frames (has %d, t_base %lld)",
+               u, kCmvnWindow, n_hist[u], (long long)t_base[u]);
+      return CE_GPU_EINVAL;
+    }
+    out_off[u + 1] = out_off[u] + (rows - n_hist[u]);
+  }
+  const int64_t total_in = utt_frame_offsets[n_utts], total_out = out_off[n_utts];
+  if (total_out == 0) return CE_GPU_OK;
+  CE_CHECK(UseDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StageWs *ws = GetWs(device);
+  const void *in_dev = nullptr;
+  CE_CHECK(StageIn(feats, sizeof(float) * (size_t)total_in * num_mel, &ws->in, s, &in_dev));
+  CE_CHECK(ws->in2.Reserve(sizeof(float) * (num_mel + 1)));
+  CE_CUDA(cudaMemcpyAsync(ws->in2.ptr, global_stats, sizeof(float) * (num_mel + 1), cudaMemcpyHostToDevice, s));
+  const size_t state_bytes = sizeof(float) * (size_t)n_utts * num_mel;
+  CE_CHECK(ws->tmp[0].Reserve(state_bytes));
+  CE_CUDA(cudaMemcpyAsync(ws->tmp[0].ptr, state, state_bytes, cudaMemcpyHostToDevice, s));
+  CE_CUDA(cudaStreamSynchronize(s));                     // global_stats / state may be reused by the caller
+  const size_t out_bytes = sizeof(float) * (size_t)total_out * num_mel;
+  float *out_dev = out;
+  if (!IsDevicePtr(out)) {
+    CE_CHECK(ws->out.Reserve(out_bytes));
+    out_dev = ws->out.as<float>();
+  }
+  CmvnResume resume = {n_hist, t_base, ws->tmp[0].as<float>()};
+  CE_CHECK(CmvnLaunch(ws->in2.as<float>(), global_stats[num_mel], static_cast<const float *>(in_dev),
+                      utt_frame_offsets, out_off.data(), n_utts, num_mel, 0, 0, out_dev, num_mel, &ws->t0, s,
+                      &resume));
+  CE_CUDA(cudaMemcpyAsync(state, ws->tmp[0].ptr, state_bytes, cudaMemcpyDeviceToHost, s));
+  CE_CHECK(Deliver(out, out_dev, out_bytes, s));
+  CE_CUDA(cudaStreamSynchronize(s));                     // the state is complete on return
+  return CE_GPU_OK;
+}
+
 int ce_gpu_rfft512(const float *in, int n_frames, float *out, int device, void *stream) {
   if (n_frames < 0 || (n_frames > 0 && (!in || !out))) {
     SetError("ce_gpu_rfft512: bad arguments");

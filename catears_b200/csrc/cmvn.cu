@@ -30,10 +30,11 @@ namespace ce {
 namespace {
 
 struct CmvnUtt {
-  int64_t in_row;    // first row of the utterance in feats
+  int64_t in_row;    // first row of the utterance's (new) frames in feats
   int64_t out_row;   // first row of the utterance's block in out (before pad_left)
-  int32_t T;
-  int32_t pad;
+  int32_t T;         // frames to normalise in this launch
+  int32_t t_base;    // frames of the utterance normalised by earlier launches (streaming; else 0):
+                     // the raw frames t_base - 600 .. t_base - 1 then precede in_row in feats
 };
 
 struct CmvnStep {    // frame-index-only part of the chain (t < 600; t >= 599 uses entry 599)
@@ -48,11 +49,12 @@ __global__ void __launch_bounds__(kCmvnThreads)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
             int mel, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
-            int64_t out_stride) {
+            int64_t out_stride, float *__restrict__ state) {
   extern __shared__ float cmvn_smem[];
   const CmvnUtt ut = utts[blockIdx.x];
   const int T = ut.T;
   if (T <= 0) return;
+  const int tb = ut.t_base;                    // absolute index of this launch's first frame
   const int TF = tile_frames;
   const int tile_elems = TF * mel;
   float *xs = cmvn_smem;                         // [2][tile_elems]
@@ -78,8 +80,8 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
     float *dx = xs + (j & 1) * tile_elems;
     float *dxo = xos + (j & 1) * tile_elems;
     const float *src = x + (int64_t)t0 * mel;
-    const bool need_old = apply && t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
-    const int first_old = (kCmvnWindow - t0) * mel;         // elements before it have t < 600
+    const bool need_old = apply && tb + t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
+    const int first_old = (kCmvnWindow - tb - t0) * mel;         // elements before it have t < 600
     float a[kPerThread], b[kPerThread];
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
@@ -107,9 +109,9 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
       const int t = t0 + tl;
       float r = dx[i];
       if (apply) {
-        const CmvnStep st = steps[min(t, kCmvnWindow - 1)];
+        const CmvnStep st = steps[min(tb + t, kCmvnWindow - 1)];
         float stat = ds[i];
-        if (t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, __ldg(g + d)));   // AddVec
+        if (tb + t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, __ldg(g + d)));   // AddVec
         r = __fadd_rn(r, __fmul_rn(st.nscale, stat));                                       // cmvn.cc:96-97
       }
       y[(int64_t)t * out_stride + d] = r;
@@ -127,6 +129,7 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   // log-mel magnitudes) the result is RN(S + d), one fp32 add; otherwise fall back to fp64.  For
   // t < 600 it is RN(S + x).  Only that add is on the dependent chain.
   float cached = 0.0f;                           // chain state of this thread's bin
+  if (state && is_chain && tid < mel) cached = state[(int64_t)blockIdx.x * mel + tid];   // streaming: resume
   if (!is_chain) load_tile(0);
   __syncthreads();
   for (int j = 0; j < n_tiles; ++j) {
@@ -137,7 +140,7 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
         const float *dx = xs + (j & 1) * tile_elems + tid;
         const float *dxo = xos + (j & 1) * tile_elems + tid;
         float *ds = ss + (j & 1) * tile_elems + tid;
-        if (t0 + TF <= kCmvnWindow) {            // no frame leaves the window yet
+        if (tb + t0 + TF <= kCmvnWindow) {       // no frame leaves the window yet
 #pragma unroll 8
           for (int tl = 0; tl < nt; ++tl) {
             cached = __fadd_rn(cached, dx[tl * mel]);
@@ -147,7 +150,7 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
 #pragma unroll 8
           for (int tl = 0; tl < nt; ++tl) {
             const float xv = dx[tl * mel];
-            if (t0 + tl >= kCmvnWindow) {
+            if (tb + t0 + tl >= kCmvnWindow) {
               const float xo = dxo[tl * mel];
               const float dh = __fsub_rn(xv, xo);                      // TwoSum(x, -x_old)
               const float bv = __fsub_rn(dh, xv);
@@ -175,6 +178,7 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
     __syncthreads();
   }
   if (!is_chain) store_tile(n_tiles - 1);
+  if (state && is_chain && tid < mel) state[(int64_t)blockIdx.x * mel + tid] = cached;
 }
 
 struct StepTable {
@@ -225,7 +229,7 @@ int GetSteps(float global_count, const CmvnStep **out) {
 int CmvnLaunch(const float *global_stats_dev, float global_count, const float *feats_dev,
                const int64_t *frame_off, const int64_t *out_row_off, int n_utts, int num_mel,
                int pad_left, int pad_right, float *out_dev, int64_t out_stride, Table *utts,
-               cudaStream_t s) {
+               cudaStream_t s, const CmvnResume *resume) {
   if (n_utts <= 0) return CE_GPU_OK;
   const CmvnStep *steps = nullptr;
   if (global_stats_dev) CE_CHECK(GetSteps(global_count, &steps));
@@ -236,7 +240,12 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
     h[u].in_row = frame_off[u];
     h[u].out_row = out_row_off[u];
     h[u].T = (int32_t)(frame_off[u + 1] - frame_off[u]);
-    h[u].pad = 0;
+    h[u].t_base = 0;
+    if (resume) {                                          // rows [frame_off[u], +n_hist) are history
+      h[u].in_row += resume->n_hist[u];
+      h[u].T -= resume->n_hist[u];
+      h[u].t_base = (int32_t)std::min<int64_t>(resume->t_base[u], 0x7fffffff);
+    }
   }
   CE_CHECK(utts->Upload(bytes, s));
   if (num_mel > kMaxMel) {
@@ -259,7 +268,7 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
   cmvn_kernel<<<(unsigned)n_utts, kCmvnThreads, smem, s>>>(global_stats_dev, steps, feats_dev,
                                                            utts->dev<CmvnUtt>(), n_utts, num_mel,
                                                            tile_frames, pad_left, pad_right, out_dev,
-                                                           out_stride);
+                                                           out_stride, resume ? resume->state_dev : nullptr);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

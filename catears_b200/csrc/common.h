@@ -143,10 +143,19 @@ int Rfft512Launch(const float *in_dev, int n_frames, float *out_dev, cudaStream_
 // pad_right > 0, the first / last frame is replicated into the padding rows
 // (src/am.cc:119-124,152-155).  global_stats_dev == nullptr: copy + pad only (no CMVN, which
 // is what src/ce_stt.cc does).
+// Streaming continuation: utterance u's rows start with n_hist[u] raw frames it has already
+// normalised (the last min(t_base[u], 600) of them, needed as x_{t-600}); the chain resumes from
+// state_dev[u * num_mel ..] (running sums, updated in place) at absolute frame index t_base[u].
+// Only the new frames are written, to out rows out_row_off[u] ...
+struct CmvnResume {
+  const int32_t *n_hist;     // host [n_utts]
+  const int64_t *t_base;     // host [n_utts]
+  float *state_dev;          // device [n_utts x num_mel]
+};
 int CmvnLaunch(const float *global_stats_dev, float global_count, const float *feats_dev,
                const int64_t *frame_off_host, const int64_t *out_row_off_host, int n_utts,
                int num_mel, int pad_left, int pad_right, float *out_dev, int64_t out_stride,
-               Table *utts, cudaStream_t s);
+               Table *utts, cudaStream_t s, const CmvnResume *resume = nullptr);
 
 }  // namespace ce
 

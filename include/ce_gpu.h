@@ -104,6 +104,19 @@ int ce_gpu_cmvn(const float *global_stats, const float *feats,
                 const int64_t *utt_frame_offsets, int n_utts, int num_mel, float *out,
                 int device, void *stream);
 
+/* The same CMVN continued across calls (streaming; the reference's CMVN::GetFrame is causal and is
+ * driven frame by frame, src/cmvn.cc:35-68).  For utterance u, rows [off[u], off[u+1]) of `feats` are
+ * n_hist[u] RAW frames that earlier calls already normalised -- exactly the last
+ * min(t_base[u], 600) of them, oldest first; they are only read as x_{t-600} -- followed by the new
+ * raw frames.  t_base[u] = frames normalised before this call.  state[u * num_mel ...] (HOST, in and
+ * out) holds the running sums after t_base[u] frames: all zeros for a new utterance.  `out` receives
+ * only the NEW frames, packed by utterance.  Bit-identical to one ce_gpu_cmvn call on the whole
+ * utterance, for any split into calls. */
+int ce_gpu_cmvn_stream(const float *global_stats, const float *feats,
+                       const int64_t *utt_frame_offsets, const int32_t *n_hist,
+                       const int64_t *t_base, float *state, int n_utts, int num_mel, float *out,
+                       int device, void *stream);
+
 /* 512-point forward real FFT of n_frames rows of 512 floats, packed output
  * [Re0, Re256, Re1, Im1, ...] as SRFFT::Compute (src/srfft.cc:370).  Test hook for the FFT
  * inside ce_gpu_fbank (the same device code). */

@@ -311,5 +311,143 @@ class AcousticModel {
   mutable Matrix scratch_;
 };
 
+// ---------------------------------------------------------------------------------------------
+// StreamBatch: many live utterances evaluated together.  Every Process() call
+// takes whatever PCM has arrived for each stream and runs ONE fbank, ONE CMVN and ONE acoustic-model
+// pass for all of them; what the reference keeps per utterance in Fbank::Instance, CMVN and
+// AcousticModel::Instance is carried here between calls:
+//   * the samples that do not fill a frame yet (< 400 + 160, src/fbank.cc:308-313),
+//   * the last <= 600 raw feature frames and the CMVN running sums (src/cmvn.cc:35-68),
+//   * the normalised frames whose right context has not arrived, behind `left_context` frames of
+//     left context (first frame replicated at the start, last frame at end of stream,
+//     src/am.cc:119-124,152-155).
+// Rows come out as soon as their right context exists; concatenated over the calls they are the rows
+// of a whole-utterance evaluation (bit-identical CMVN; float log-likelihoods identical row by row --
+// for int8 models the Quantize granularity is the micro-batch, as it is the chunk in the reference).
+// ---------------------------------------------------------------------------------------------
+class StreamBatch {
+ public:
+  struct Stream {
+    std::vector<int16_t> wave;       // samples not yet framed
+    std::vector<float> raw_hist;     // last <= 600 raw fbank frames [n x mel]
+    std::vector<float> cmvn_state;   // running sums [mel]
+    int64_t frames_normalised = 0;
+    std::vector<float> ctx;          // normalised frames buffered for the AM [n x mel]
+    bool started = false, ended = false;
+    int64_t rows_emitted = 0;
+  };
+
+  // global_cmvn_stats: mel sums + count, or empty for no CMVN (what src/ce_stt.cc does).
+  StreamBatch(const AcousticModel *am, const std::vector<float> &global_cmvn_stats, int device = 0)
+      : am_(am), stats_(global_cmvn_stats), device_(device) {}
+
+  // pcm[i] / n_samples[i]: new audio of streams[i] (may be 0); end_of_stream[i]: no more audio will
+  // come.  rows[i] receives the log-likelihood rows that became ready (0 rows if none).
+  Status Process(const std::vector<Stream *> &streams, const std::vector<const int16_t *> &pcm,
+                 const std::vector<int> &n_samples, const std::vector<bool> &end_of_stream,
+                 std::vector<Matrix> *rows) const {
+    const int n = (int)streams.size(), mel = am_->feat_dim(), P = am_->num_pdfs();
+    const int L = am_->left_context(), R = am_->right_context();
+    rows->assign(n, Matrix());
+    // ---- 1. fbank of every stream's buffered samples, one call ----
+    std::vector<int16_t> all_pcm;
+    std::vector<int64_t> soff(n + 1, 0), foff(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+      Stream *st = streams[i];
+      if (st->ended) return Status::RuntimeError("StreamBatch: stream already ended");
+      if (n_samples[i] > 0) st->wave.insert(st->wave.end(), pcm[i], pcm[i] + n_samples[i]);
+      all_pcm.insert(all_pcm.end(), st->wave.begin(), st->wave.end());
+      soff[i + 1] = (int64_t)all_pcm.size();
+    }
+    const int64_t new_frames = ce_gpu_frame_offsets(soff.data(), n, foff.data());
+    if (new_frames < 0) return Status::FromGpu((int)new_frames);
+    std::vector<float> raw((size_t)new_frames * mel);
+    if (new_frames > 0) {
+      int rc = ce_gpu_fbank(all_pcm.data(), soff.data(), n, mel, raw.data(), device_, nullptr);
+      if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    }
+    for (int i = 0; i < n; ++i) {
+      const int64_t f = foff[i + 1] - foff[i];
+      Stream *st = streams[i];
+      st->wave.erase(st->wave.begin(), st->wave.begin() + f * 160);
+    }
+    // ---- 2. CMVN continued from every stream's state, one call ----
+    std::vector<float> norm = raw;
+    if (!stats_.empty() && new_frames > 0) {
+      std::vector<float> in, state((size_t)n * mel, 0.0f);
+      std::vector<int64_t> coff(n + 1, 0), tbase(n);
+      std::vector<int32_t> nhist(n);
+      for (int i = 0; i < n; ++i) {
+        Stream *st = streams[i];
+        if (st->cmvn_state.empty()) st->cmvn_state.assign(mel, 0.0f);
+        nhist[i] = (int32_t)(st->raw_hist.size() / mel);
+        tbase[i] = st->frames_normalised;
+        in.insert(in.end(), st->raw_hist.begin(), st->raw_hist.end());
+        in.insert(in.end(), raw.begin() + foff[i] * mel, raw.begin() + foff[i + 1] * mel);
+        coff[i + 1] = (int64_t)(in.size() / mel);
+        std::copy(st->cmvn_state.begin(), st->cmvn_state.end(), state.begin() + (size_t)i * mel);
+      }
+      int rc = ce_gpu_cmvn_stream(stats_.data(), in.data(), coff.data(), nhist.data(), tbase.data(), state.data(),
+                                  n, mel, norm.data(), device_, nullptr);
+      if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+      for (int i = 0; i < n; ++i) {
+        Stream *st = streams[i];
+        std::copy(state.begin() + (size_t)i * mel, state.begin() + (size_t)(i + 1) * mel, st->cmvn_state.begin());
+        st->raw_hist.insert(st->raw_hist.end(), raw.begin() + foff[i] * mel, raw.begin() + foff[i + 1] * mel);
+        const size_t keep = (size_t)600 * mel;
+        if (st->raw_hist.size() > keep) st->raw_hist.erase(st->raw_hist.begin(), st->raw_hist.end() - keep);
+        st->frames_normalised += foff[i + 1] - foff[i];
+      }
+    }
+    // ---- 3. acoustic model on every stream's rows whose context is complete, one call ----
+    std::vector<float> x;
+    std::vector<int64_t> xoff(1, 0);
+    std::vector<int> who, ready;
+    for (int i = 0; i < n; ++i) {
+      Stream *st = streams[i];
+      const float *f0 = norm.data() + foff[i] * mel;
+      const int64_t f = foff[i + 1] - foff[i];
+      if (f > 0 && !st->started) {                           // left padding, src/am.cc:119-124
+        for (int k = 0; k < L; ++k) st->ctx.insert(st->ctx.end(), f0, f0 + mel);
+        st->started = true;
+      }
+      st->ctx.insert(st->ctx.end(), f0, f0 + f * mel);
+      if (end_of_stream[i]) {
+        st->ended = true;
+        if (!st->ctx.empty()) {                              // right padding, src/am.cc:152-155
+          const std::vector<float> last(st->ctx.end() - mel, st->ctx.end());
+          for (int k = 0; k < R; ++k) st->ctx.insert(st->ctx.end(), last.begin(), last.end());
+        }
+      }
+      const int have = (int)(st->ctx.size() / mel);
+      const int n_ready = have - L - R;
+      if (n_ready <= 0) continue;
+      x.insert(x.end(), st->ctx.begin(), st->ctx.begin() + (size_t)(n_ready + L + R) * mel);
+      xoff.push_back((int64_t)(x.size() / mel));
+      who.push_back(i);
+      ready.push_back(n_ready);
+    }
+    if (who.empty()) return Status::OK();
+    std::vector<float> ll((size_t)xoff.back() * P);
+    int rc = ce_gpu_nnet(am_->handle(), x.data(), xoff.data(), (int)who.size(), ll.data(), nullptr, nullptr);
+    if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    for (size_t k = 0; k < who.size(); ++k) {
+      Stream *st = streams[who[k]];
+      Matrix &out = (*rows)[who[k]];
+      out.Resize(ready[k], P);
+      memcpy(out.data.data(), ll.data() + (size_t)(xoff[k] + L) * P, sizeof(float) * (size_t)ready[k] * P);
+      st->ctx.erase(st->ctx.begin(), st->ctx.begin() + (size_t)ready[k] * mel);
+      st->rows_emitted += ready[k];
+      if (st->ended) st->ctx.clear();
+    }
+    return Status::OK();
+  }
+
+ private:
+  const AcousticModel *am_;
+  std::vector<float> stats_;
+  int device_;
+};
+
 }  // namespace ce_host
 #endif  // CE_HOST_HPP_

@@ -4,6 +4,7 @@
 //
 //   host_mirror_test errors
 //   host_mirror_test stream <conf> <pcm.s16le> <out.bin> <precision 0..3> [cmvn_stats.vec0]
+//   host_mirror_test streams <conf> <precision> <cmvn_stats.vec0 | -> <seed> <out_prefix> <pcm>...
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -111,9 +112,82 @@ static int Stream(int argc, char **argv) {
   return 0;
 }
 
+// streams <conf> <precision> <cmvn_stats.vec0 | -> <seed> <out_prefix> <pcm.s16le>...
+// Several live utterances fed in random-sized pieces through ONE StreamBatch; writes
+// <out_prefix>.<i>.bin with the rows of stream i in the order they came out.
+static int Streams(int argc, char **argv) {
+  const std::string conf = argv[2], stats_path = argv[4], prefix = argv[6];
+  const int precision = atoi(argv[3]);
+  uint64_t rng = strtoull(argv[5], nullptr, 10) * 2654435761ull + 12345;
+  auto next = [&rng]() {
+    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(rng >> 33);
+  };
+  AcousticModel am;
+  Status st = am.Read(conf, precision, 0);
+  if (!st.ok()) return Fail("AcousticModel::Read", st);
+  std::vector<float> stats;
+  if (stats_path != "-") {
+    st = detail::ReadVec0<float>(stats_path, &stats);
+    if (!st.ok()) return Fail("cmvn stats", st);
+  }
+  const int n = argc - 7;
+  std::vector<std::vector<int16_t>> audio(n);
+  for (int i = 0; i < n; ++i) {
+    FILE *f = fopen(argv[7 + i], "rb");
+    if (!f) return Fail("open pcm", Status::IOError(argv[7 + i]));
+    int16_t buf[4096];
+    size_t got;
+    while ((got = fread(buf, 2, 4096, f)) > 0) audio[i].insert(audio[i].end(), buf, buf + got);
+    fclose(f);
+  }
+  StreamBatch batch(&am, stats, 0);
+  std::vector<StreamBatch::Stream> state(n);
+  std::vector<size_t> pos(n, 0);
+  std::vector<std::vector<float>> rows(n);
+  int calls = 0, live = n;
+  while (live > 0) {
+    std::vector<StreamBatch::Stream *> streams;
+    std::vector<const int16_t *> pcm;
+    std::vector<int> cnt;
+    std::vector<bool> eos;
+    std::vector<int> idx;
+    for (int i = 0; i < n; ++i) {
+      if (state[i].ended) continue;
+      size_t take = next() % 3 == 0 ? 0 : next() % 9000;     // sometimes nothing arrives
+      take = std::min(take, audio[i].size() - pos[i]);
+      streams.push_back(&state[i]);
+      pcm.push_back(audio[i].data() + pos[i]);
+      cnt.push_back((int)take);
+      pos[i] += take;
+      eos.push_back(pos[i] == audio[i].size());
+      idx.push_back(i);
+    }
+    std::vector<Matrix> out;
+    st = batch.Process(streams, pcm, cnt, eos, &out);
+    if (!st.ok()) return Fail("StreamBatch::Process", st);
+    for (size_t k = 0; k < idx.size(); ++k) {
+      rows[idx[k]].insert(rows[idx[k]].end(), out[k].data.begin(), out[k].data.end());
+      if (state[idx[k]].ended) --live;
+    }
+    ++calls;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int32_t hdr[3] = {(int32_t)(rows[i].size() / am.num_pdfs()), am.num_pdfs(), calls};
+    FILE *o = fopen((prefix + "." + std::to_string(i) + ".bin").c_str(), "wb");
+    if (!o) return Fail("open out", Status::IOError(prefix));
+    fwrite(hdr, 4, 3, o);
+    fwrite(rows[i].data(), 4, rows[i].size(), o);
+    fclose(o);
+  }
+  printf("OK streams=%d calls=%d\n", n, calls);
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc >= 2 && strcmp(argv[1], "errors") == 0) return Errors();
   if (argc >= 6 && strcmp(argv[1], "stream") == 0) return Stream(argc, argv);
+  if (argc >= 8 && strcmp(argv[1], "streams") == 0) return Streams(argc, argv);
   fprintf(stderr, "usage: %s errors | stream <conf> <pcm> <out> <precision> [cmvn_stats]\n", argv[0]);
   return 2;
 }

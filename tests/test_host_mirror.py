@@ -89,3 +89,70 @@ def test_host_mirror_int8_matches_batch_api(exe, tmp_path, golden):
     whole, _ = am.nnet(padded)
     am.close()
     assert np.array_equal(got, whole[L:L + 47])
+
+
+@pytest.mark.gpu
+def test_stream_batch_micro_batches_equal_whole_utterances(exe, tmp_path, golden):
+    """five live utterances (0.5 s to 12 s, one shorter than a frame) arrive in
+    random-sized pieces and are evaluated together, one fbank / CMVN / AM pass per call, with the
+    sample remainder, the CMVN sums + 600-frame history and the AM context carried between calls.
+    Per stream the concatenated rows must equal the whole-utterance evaluation: the CMVN is
+    bit-identical by construction, the fp32 log-likelihoods agree to 1e-5."""
+    stats = golden["cmvn_stats"]
+    m = synth.write_model(str(tmp_path / "m"), name="small", hidden=64, num_pdfs=96, seed=4321, cmvn_stats=stats)
+    stats_path = str(tmp_path / "stats.vec0")
+    F.write_vector(stats_path, stats)
+    lengths = [8000, 192000, 300, 47001, 112345]              # 12 s > 600 frames: the CMVN window slides
+    pcms, paths = [], []
+    for i, n in enumerate(lengths):
+        pcm = synth.synth_utterance(40 + i, n)
+        pcms.append(pcm)
+        paths.append(str(tmp_path / ("s%d.s16le" % i)))
+        pcm.astype("<i2").tofile(paths[-1])
+    prefix = str(tmp_path / "rows")
+    for seed in (1, 2):
+        r = subprocess.run([exe, "streams", m["conf"], str(api.PRECISION_FP32), stats_path, str(seed), prefix] + paths,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        am = api.AcousticModelGpu(config=m["conf"], precision="fp32")
+        for i, pcm in enumerate(pcms):
+            raw = np.fromfile("%s.%d.bin" % (prefix, i), np.int32, 3)
+            got = np.fromfile("%s.%d.bin" % (prefix, i), np.float32, offset=12).reshape(int(raw[0]), int(raw[1]))
+            frames = 0 if pcm.size < 400 else 1 + (pcm.size - 400) // 160
+            assert got.shape == (frames, 96), (i, got.shape)
+            assert int(raw[2]) > 3                               # really several micro-batches
+            if frames:
+                whole, _, _ = am.forward(pcm)
+                assert np.abs(got - whole).max() < 1e-5, i
+        am.close()
+
+
+@pytest.mark.gpu
+def test_cmvn_stream_is_bit_identical_for_any_split(golden):
+    """ce_gpu_cmvn_stream: 1500 frames normalised in pieces of every size (1 .. 700 frames), two
+    utterances at once, equal bit for bit to one ce_gpu_cmvn call."""
+    rng = np.random.default_rng(8)
+    stats = golden["cmvn_stats"]
+    feats = [(12.0 + 4.0 * rng.standard_normal((1500, 40))).astype(np.float32),
+             (9.0 + 2.0 * rng.standard_normal((777, 40))).astype(np.float32)]
+    want = [api.cmvn(stats, f) for f in feats]
+    state = np.zeros((2, 40), np.float32)
+    t = [0, 0]
+    got = [[], []]
+    while t[0] < 1500 or t[1] < 777:
+        step = [int(rng.integers(0, 700)), int(rng.integers(0, 300))]
+        parts, nh, off = [], [], [0]
+        for u in range(2):
+            step[u] = min(step[u], feats[u].shape[0] - t[u])
+            h = min(t[u], 600)
+            parts.append(feats[u][t[u] - h:t[u] + step[u]])
+            nh.append(h)
+            off.append(off[-1] + h + step[u])
+        out = api.cmvn_stream(stats, np.concatenate(parts), off, nh, t, state)
+        a = 0
+        for u in range(2):
+            got[u].append(out[a:a + step[u]])
+            a += step[u]
+            t[u] += step[u]
+    for u in range(2):
+        assert np.array_equal(np.concatenate(got[u]), want[u]), u
