@@ -475,8 +475,12 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     int64_t rows = 0;
     // Host PCM arrives over PCIe behind the compute: a short first chunk (a quarter of the cap)
     // keeps the copy nobody can hide short; every later copy runs under the previous chunk.
-    const int64_t cap = (all.pcm_host && chunk == 0) ? std::max<int64_t>(kTileM, m->max_chunk_rows / 4)
-                                                      : m->max_chunk_rows;
+    // Inputs that are already in HBM have no copy to hide, so they run in chunks twice as large
+    // (fewer launch ramps and tails: 15.4 -> 15.0 ms per step on the bench batch; for host input
+    // larger later chunks were measured to bring nothing).
+    const int64_t cap = !all.pcm_host ? 2 * m->max_chunk_rows
+                        : chunk == 0  ? std::max<int64_t>(kTileM, m->max_chunk_rows / 4)
+                                      : m->max_chunk_rows;
     while (u1 < n_utts) {
       const int64_t T = frame_off[u1 + 1] - frame_off[u1];
       const int64_t r = T > 0 ? (T + L + R + kTileM - 1) / kTileM * kTileM : 0;

@@ -39,7 +39,8 @@ struct ce_gpu_model {
   ce::DevBuf cmvn_dev;
   // Rows of activations evaluated per pass of the layer stack (CE_GPU_CHUNK_ROWS).  Large chunks
   // amortise the per-launch ramp and tail of every kernel; a batch above the cap runs as several
-  // chunks, which is also the granularity at which host PCM is copied in behind the compute.
+  // chunks, which is also the granularity at which host PCM is copied in behind the compute
+  // (device-resident inputs use twice this cap, see ForwardAll).
   int64_t max_chunk_rows = 131072;
 
   // ---- workspace (one forward call at a time per handle) ----
