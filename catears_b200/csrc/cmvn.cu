@@ -24,7 +24,10 @@
 #include <map>
 #include <mutex>
 
+#include <float.h>
+
 #include "common.h"
+#include "gemm.h"
 
 namespace ce {
 namespace {
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(kCmvnThreads)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
             int mel, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
-            int64_t out_stride, float *__restrict__ state) {
+            int64_t out_stride, float *__restrict__ state, uint32_t *__restrict__ minmax) {
   extern __shared__ float cmvn_smem[];
   const CmvnUtt ut = utts[blockIdx.x];
   const int T = ut.T;
@@ -98,6 +101,7 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
       }
     }
   };
+  float wmin = FLT_MAX, wmax = -FLT_MAX;         // FindMinMax of what this thread writes (matrix.cc:329-345)
   auto store_tile = [&](int j) {                 // workers: y for tile j, and the replicated edges
     const int t0 = j * TF;
     const int n = min(TF, T - t0) * mel;
@@ -115,6 +119,8 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
         r = __fadd_rn(r, __fmul_rn(st.nscale, stat));                                       // cmvn.cc:96-97
       }
       y[(int64_t)t * out_stride + d] = r;
+      wmin = (r < wmin) ? r : wmin;
+      wmax = (r > wmax) ? r : wmax;
       if (t == 0)
         for (int p = 1; p <= pad_left; ++p) y[-(int64_t)p * out_stride + d] = r;
       if (t == T - 1)
@@ -179,6 +185,17 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   }
   if (!is_chain) store_tile(n_tiles - 1);
   if (state && is_chain && tid < mel) state[(int64_t)blockIdx.x * mel + tid] = cached;
+  if (minmax && !is_chain) {                     // the utterance's min/max for the first Quantize
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+      wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    }
+    if ((tid & 31) == 0 && wmin <= wmax) {
+      atomicMin(minmax + 2 * blockIdx.x, OrderedFromFloat(wmin));
+      atomicMax(minmax + 2 * blockIdx.x + 1, OrderedFromFloat(wmax));
+    }
+  }
 }
 
 struct StepTable {
@@ -229,7 +246,7 @@ int GetSteps(float global_count, const CmvnStep **out) {
 int CmvnLaunch(const float *global_stats_dev, float global_count, const float *feats_dev,
                const int64_t *frame_off, const int64_t *out_row_off, int n_utts, int num_mel,
                int pad_left, int pad_right, float *out_dev, int64_t out_stride, Table *utts,
-               cudaStream_t s, const CmvnResume *resume) {
+               cudaStream_t s, const CmvnResume *resume, uint32_t *minmax_dev) {
   if (n_utts <= 0) return CE_GPU_OK;
   const CmvnStep *steps = nullptr;
   if (global_stats_dev) CE_CHECK(GetSteps(global_count, &steps));
@@ -268,7 +285,7 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
   cmvn_kernel<<<(unsigned)n_utts, kCmvnThreads, smem, s>>>(global_stats_dev, steps, feats_dev,
                                                            utts->dev<CmvnUtt>(), n_utts, num_mel,
                                                            tile_frames, pad_left, pad_right, out_dev,
-                                                           out_stride, resume ? resume->state_dev : nullptr);
+                                                           out_stride, resume ? resume->state_dev : nullptr, minmax_dev);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

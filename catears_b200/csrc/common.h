@@ -155,7 +155,9 @@ struct CmvnResume {
 int CmvnLaunch(const float *global_stats_dev, float global_count, const float *feats_dev,
                const int64_t *frame_off_host, const int64_t *out_row_off_host, int n_utts,
                int num_mel, int pad_left, int pad_right, float *out_dev, int64_t out_stride,
-               Table *utts, cudaStream_t s, const CmvnResume *resume = nullptr);
+               Table *utts, cudaStream_t s, const CmvnResume *resume = nullptr,
+               uint32_t *minmax_dev = nullptr);   // [n_utts][2] ordered-int min/max of the rows written
+                                                  // (initialised by the caller), nullptr = off
 
 }  // namespace ce
 

@@ -306,18 +306,20 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     feat_off = local_off.data();
   }
 
-  // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155 ----
-  CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
-                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, feat_off, row_off64.data(),
-                      n_utts, F, L, R, w->x0.as<float>(), F, &w->cmvn_utts, s));
-
-  // ---- network input in the operand format of the data path ----
+  // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155.  For the u8 path the same
+  // kernel reduces each utterance's min/max (the padding rows are copies, so the frames' min/max is
+  // the matrix's) for the first Quantize. ----
   uint32_t *mm = w->minmax.as<uint32_t>();
   QParam *qp = w->qparams.as<QParam>();
+  if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
+  CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
+                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, feat_off, row_off64.data(),
+                      n_utts, F, L, R, w->x0.as<float>(), F, &w->cmvn_utts, s, nullptr,
+                      m->kind == kKindI8 ? mm : nullptr));
+
+  // ---- network input in the operand format of the data path ----
   const int c0 = m->blocks[0].c_pad;
   if (m->kind == kKindI8) {
-    CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
-    CE_CHECK(MinMaxLaunch(w->x0.as<float>(), F, F, M, d_tile, d_utts, MakeRowUse(m, -1), mm, s));
     CE_CHECK(QuantizeLaunch(w->x0.as<float>(), F, F, M, c0, d_tile, mm, n_utts, qp,
                             w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
   } else if (m->kind == kKindBF16) {
