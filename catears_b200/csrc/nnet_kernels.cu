@@ -237,8 +237,11 @@ quantize_rows_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, i
   const int u_end = (int)((int64_t)n_units * (blockIdx.x + 1) / gridDim.x);
   const int n_rows = (u_end - u_begin) * kQuantRowsPerWarp;           // rows of this warp
   if (n_rows <= 0) return;
+  // Units are walked from the END of the matrix: the producing GEMM wrote its last ~100 MB of fp32
+  // most recently (still in L2), and the consuming GEMM starts reading the codes at row 0, which are
+  // then the ones written last.
   auto row_of = [&](int i) {
-    return (u_begin + i / kQuantRowsPerWarp) * kQuantUnitRows + warp * kQuantRowsPerWarp +
+    return (n_units - 1 - (u_begin + i / kQuantRowsPerWarp)) * kQuantUnitRows + warp * kQuantRowsPerWarp +
            (i % kQuantRowsPerWarp);
   };
   auto load_row = [&](int row, float4 (&buf)[NV]) {
@@ -420,7 +423,9 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
                          int64_t ld_out, int32_t *__restrict__ argmax) {
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
-  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
+  // rows are walked from the end: the output-layer GEMM wrote those last (L2)
+  for (int rr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < M; rr += warps) {
+  const int row = M - 1 - rr;
   const int utt = tile_utt[row / kTileM];
   const UttRows ur = utts[utt];
   const int pos = row - ur.row_off;
