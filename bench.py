@@ -377,7 +377,12 @@ def run_gpu(args):
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("gemm_%s_dram_bytes_per_launch" % args.precision)
+        per_row = json.load(open(tr_path)).get("gemm_%s_dram_bytes_per_row" % args.precision)
+        if per_row and gemm_n:
+            # ncu measured one hidden-layer launch; scale its bytes per activation row (1024 rows
+            # per 10 s utterance) to the rows one launch of this run's chunking covers
+            launches_per_step = gemm_n / max(1, args.steps)
+            traffic = int(per_row * n_utts * 1024 / max(1.0, launches_per_step / 7.0))
     achieved = flops_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
         "kernel": "gemm_kernel<%s> (tcgen05 cta_group::2, %d launches/step)" % (args.precision, gemm_n // max(1, args.steps)),
