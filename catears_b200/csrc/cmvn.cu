@@ -77,27 +77,36 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   // mel <= 128: exact with a 20-bit reciprocal).  Every load of a tile is issued before any is used.
   const uint32_t inv_mel = ((1u << 20) + mel - 1) / mel;
   constexpr int kPerThread = 16;                 // >= tile_elems / n_workers for every configuration
-  auto load_tile = [&](int j) {                  // workers: global -> smem, tile j
+  // Loading a tile is split in two so that its latency hides behind the stores of the previous tile:
+  // fetch_tile issues every load into registers, commit_tile writes them to shared memory once the
+  // buffer is free.
+  float la[kPerThread], lb[kPerThread];
+  auto fetch_tile = [&](int j) {                 // workers: global -> registers, tile j
+    const int t0 = j * TF;
+    const int n = min(TF, T - t0) * mel;
+    const float *src = x + (int64_t)t0 * mel;
+    const bool need_old = apply && tb + t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
+    const int first_old = (kCmvnWindow - tb - t0) * mel;         // elements before it have t < 600
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      const int i = wtid + k * n_workers;
+      la[k] = (i < n) ? __ldg(src + i) : 0.0f;
+      lb[k] = (need_old && i < n && i >= first_old) ? __ldg(src + i - kCmvnWindow * mel) : 0.0f;
+    }
+    asm volatile("" ::: "memory");               // the loads are issued here, not where they are used
+  };
+  auto commit_tile = [&](int j) {                // workers: registers -> smem, tile j
     const int t0 = j * TF;
     const int n = min(TF, T - t0) * mel;
     float *dx = xs + (j & 1) * tile_elems;
     float *dxo = xos + (j & 1) * tile_elems;
-    const float *src = x + (int64_t)t0 * mel;
-    const bool need_old = apply && tb + t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
-    const int first_old = (kCmvnWindow - tb - t0) * mel;         // elements before it have t < 600
-    float a[kPerThread], b[kPerThread];
-#pragma unroll
-    for (int k = 0; k < kPerThread; ++k) {
-      const int i = wtid + k * n_workers;
-      a[k] = (i < n) ? __ldg(src + i) : 0.0f;
-      b[k] = (need_old && i < n && i >= first_old) ? __ldg(src + i - kCmvnWindow * mel) : 0.0f;
-    }
+    const bool need_old = apply && tb + t0 + TF > kCmvnWindow;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
       const int i = wtid + k * n_workers;
       if (i < n) {
-        dx[i] = a[k];
-        if (need_old) dxo[i] = b[k];
+        dx[i] = la[k];
+        if (need_old) dxo[i] = lb[k];
       }
     }
   };
@@ -136,7 +145,10 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   // t < 600 it is RN(S + x).  Only that add is on the dependent chain.
   float cached = 0.0f;                           // chain state of this thread's bin
   if (state && is_chain && tid < mel) cached = state[(int64_t)blockIdx.x * mel + tid];   // streaming: resume
-  if (!is_chain) load_tile(0);
+  if (!is_chain) {
+    fetch_tile(0);
+    commit_tile(0);
+  }
   __syncthreads();
   for (int j = 0; j < n_tiles; ++j) {
     if (is_chain) {
@@ -177,9 +189,10 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
         }
       }
     } else {
+      if (j + 1 < n_tiles) fetch_tile(j + 1);    // in flight during the stores below
       if (j > 0) store_tile(j - 1);              // reads buffers (j-1)&1 ...
       asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory");
-      if (j + 1 < n_tiles) load_tile(j + 1);     // ... which tile j+1 then overwrites
+      if (j + 1 < n_tiles) commit_tile(j + 1);   // ... which tile j+1 then overwrites
     }
     __syncthreads();
   }
