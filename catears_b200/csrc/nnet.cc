@@ -44,6 +44,11 @@ ce_gpu_model::~ce_gpu_model() {
   if (call_start) cudaEventDestroy(call_start);
   for (cudaEvent_t e : copy_done) cudaEventDestroy(e);
   if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (d2h_stream) cudaStreamDestroy(d2h_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ll_ready[i]) cudaEventDestroy(ll_ready[i]);
+    if (ll_copied[i]) cudaEventDestroy(ll_copied[i]);
+  }
 }
 
 namespace ce {
@@ -200,6 +205,11 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
   CE_CUDA(cudaEventCreateWithFlags(&m->inputs_ready, cudaEventDisableTiming));
   CE_CUDA(cudaEventCreateWithFlags(&m->call_start, cudaEventDisableTiming));
   CE_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  CE_CUDA(cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CE_CUDA(cudaEventCreateWithFlags(&m->ll_ready[i], cudaEventDisableTiming));
+    CE_CUDA(cudaEventCreateWithFlags(&m->ll_copied[i], cudaEventDisableTiming));
+  }
   return CE_GPU_OK;
 }
 
@@ -471,6 +481,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   const int64_t total_frames = frame_off[n_utts] - frame_off[0];
   if (am_host) CE_CHECK(m->stage_argmax_all.Reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total_frames, 1)));
   bool used[2] = {false, false};
+  bool ll_pending[2] = {false, false};
   int u0 = 0, chunk = 0;
   while (u0 < n_utts) {
     int u1 = u0;
@@ -499,9 +510,11 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     const int64_t f0 = frame_off[u0], nf = frame_off[u1] - f0;
     float *ll_dev = loglik;
     int32_t *am_dev = argmax;
+    ce::DevBuf *ll_stage = &m->ws[chunk & 1].stage_loglik;   // two staging buffers, alternating
     if (ll_host) {
-      CE_CHECK(w->stage_loglik.Reserve(sizeof(float) * (size_t)nf * NP));
-      ll_dev = w->stage_loglik.as<float>() - f0 * NP;     // row f0 lands on the staging buffer's row 0
+      if (ll_pending[chunk & 1]) CE_CUDA(cudaStreamWaitEvent(cs, m->ll_copied[chunk & 1], 0));   // buffer free again
+      CE_CHECK(ll_stage->Reserve(sizeof(float) * (size_t)nf * NP));
+      ll_dev = ll_stage->as<float>() - f0 * NP;           // row f0 lands on the staging buffer's row 0
     }
     if (am_host) am_dev = m->stage_argmax_all.as<int32_t>() - frame_off[0];   // whole batch, one copy at the end
     PcmSource src = all;
@@ -519,9 +532,13 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     }
     CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
                           overlap ? w->stream_hi : cs));
-    if (ll_host && nf > 0) {
-      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, w->stage_loglik.ptr, sizeof(float) * (size_t)nf * NP,
-                              cudaMemcpyDeviceToHost, cs));
+    if (ll_host && nf > 0) {                               // off the compute stream: the next chunk starts now
+      CE_CUDA(cudaEventRecord(m->ll_ready[chunk & 1], cs));
+      CE_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ll_ready[chunk & 1], 0));
+      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, ll_stage->ptr, sizeof(float) * (size_t)nf * NP,
+                              cudaMemcpyDeviceToHost, m->d2h_stream));
+      CE_CUDA(cudaEventRecord(m->ll_copied[chunk & 1], m->d2h_stream));
+      ll_pending[chunk & 1] = true;
     }
     u0 = u1;
     ++chunk;
@@ -533,6 +550,8 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CUDA(cudaStreamWaitEvent(s, m->ws[i].done, 0));
     }
   }
+  for (int i = 0; i < 2; ++i)
+    if (ll_pending[i]) CE_CUDA(cudaStreamWaitEvent(s, m->ll_copied[i], 0));
   if (am_host && total_frames > 0) {
     CE_CUDA(cudaMemcpyAsync(argmax + frame_off[0], m->stage_argmax_all.ptr, sizeof(int32_t) * (size_t)total_frames,
                             cudaMemcpyDeviceToHost, s));

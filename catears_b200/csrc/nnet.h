@@ -74,6 +74,10 @@ struct ce_gpu_model {
   // Host PCM is copied chunk by chunk on its own stream so that chunk k+1 arrives while chunk k
   // is being computed.
   cudaStream_t copy_stream = nullptr;
+  // Host log-likelihood output: chunk k's rows leave over PCIe on d2h_stream (from one of two
+  // staging buffers) while chunk k+1 is computed -- the row ring a CPU decoder is fed from.
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ll_ready[2] = {nullptr, nullptr}, ll_copied[2] = {nullptr, nullptr};
   cudaEvent_t call_start = nullptr;
   std::vector<cudaEvent_t> copy_done;
   ce::DevBuf acc_dump;
