@@ -169,3 +169,38 @@ def test_unsupported_stack_is_reported(tmp_path):
     F.write_vector(prior, np.full(8, 0.125, np.float32))
     with pytest.raises(api.CeGpuError, match="Splice must be followed"):
         api.AcousticModelGpu(nnet=nnet, prior=prior, left_context=1, right_context=1)
+
+
+def test_two_handles_two_threads_concurrently(small_model, port):
+    """include/ce_gpu.h: distinct handles are independent.  Two host threads, each with its own
+    model handle and CUDA stream on the same device, run the whole path at the same time; both get
+    the result of a lone run, bit for bit (int8)."""
+    import threading
+
+    import torch
+    pcm, off = synth.synth_batch(6, 16000 * 3)
+    lone = api.AcousticModelGpu(config=small_model["conf"], precision="int8")
+    want_ll, want_am, _ = lone.forward(pcm, off)
+    lone.close()
+    results, errors = {}, []
+
+    def work(tag):
+        try:
+            m = api.AcousticModelGpu(config=small_model["conf"], precision="int8")
+            s = torch.cuda.Stream()
+            for _ in range(5):
+                ll, am, _ = m.forward(pcm, off, stream=s)
+            results[tag] = (ll, am)
+            m.close()
+        except Exception as e:          # surfaced in the main thread below
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tag in (0, 1):
+        assert np.array_equal(results[tag][0], want_ll)
+        assert np.array_equal(results[tag][1], want_am)
