@@ -143,8 +143,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Relaxed: this arrive only hands a TMEM accumulator stage back to the MMA thread -- no memory written
+// by this warp is consumed through it (tcgen05.fence::before_thread_sync orders the TMEM reads), and
+// a release at cluster scope costs a full memory barrier per tile and warp.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: data lands in THIS CTA's smem, the bytes are counted on the leader's barrier.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar,
@@ -307,8 +310,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   constexpr int kStages = C::kStages;
   constexpr int kBBytes = C::kBBytes;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the __shared__ array, not by integer arithmetic on a generic
+  // pointer: the compiler then knows every access below is shared memory and emits LDS / STS instead
+  // of generic loads and stores (which also wait on the long scoreboard).
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char *smem_a = smem;                                   // [kStages][kABytes]
   unsigned char *smem_b = smem + kStages * kABytes;               // [kStages][kBBytes]
   unsigned char *smem_out = smem + C::kOffStage;                  // [kEpiWarps][kOutTileBytes]
@@ -470,6 +475,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
 
       // ---- per-tile constants; per-column parameters -> shared memory ----
+      // (the independent loads first, so that they are in flight under the dependent
+      // tile -> utterance -> parameters chain and the barrier below)
+      int32_t rs = 0;
+      if (KIND == kKindI8) {
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int r = my_row + p.tap_off[t];
+          if (r >= 0 && r < p.M) rs += __ldg(p.a_rowsum + r);
+        }
+      }
+      const int pcol_param = n0 + et;                    // parameter arrays are padded to kTileN
+      const float bias_v = p.bias ? __ldg(p.bias + pcol_param) : 0.0f;
+      const float bns_v = p.bn_scale ? __ldg(p.bn_scale + pcol_param) : 1.0f;
+      const float bno_v = p.bn_offset ? __ldg(p.bn_offset + pcol_param) : 0.0f;
+      const int32_t colsum_v = (KIND == kKindI8) ? __ldg(p.b_colsum + pcol_param) : 0;
       const int utt = p.tile_utt ? p.tile_utt[min(m0 / kTileM, row_tiles - 1)] : 0;
       int32_t zp_a = 0;
       RowConst rc;
@@ -484,22 +503,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       }
       epi_bar();                                         // previous tile's parameters are no longer read
       {
-        const int col = n0 + et;                         // parameter arrays are padded to kTileN
-        sp[et] = p.bias ? __ldg(p.bias + col) : 0.0f;
-        sp[kTileN + et] = p.bn_scale ? __ldg(p.bn_scale + col) : 1.0f;
-        sp[2 * kTileN + et] = p.bn_offset ? __ldg(p.bn_offset + col) : 0.0f;
-        int32_t corr = 0;
-        if (KIND == kKindI8) corr = kzz - zp_a * __ldg(p.b_colsum + col);
-        reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = corr;
+        sp[et] = bias_v;
+        sp[kTileN + et] = bns_v;
+        sp[2 * kTileN + et] = bno_v;
+        reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = (KIND == kKindI8) ? kzz - zp_a * colsum_v : 0;
       }
-      if (KIND == kKindI8) {
-        int32_t rs = 0;
-        for (int t = 0; t < p.n_taps; ++t) {
-          const int r = my_row + p.tap_off[t];
-          if (r >= 0 && r < p.M) rs += __ldg(p.a_rowsum + r);
-        }
-        rc.row_corr = p.zp_b * rs;
-      }
+      if (KIND == kKindI8) rc.row_corr = p.zp_b * rs;
       bool use_row = false;                              // takes part in the fused FindMinMax
       if (p.minmax) {
         int pos = my_row, P = p.M;
