@@ -477,11 +477,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       // ---- per-tile constants; per-column parameters -> shared memory ----
       // (the independent loads first, so that they are in flight under the dependent
       // tile -> utterance -> parameters chain and the barrier below)
-      int32_t rs = 0;
+      int32_t rs = 0, rs1 = 0, rs2 = 0;                  // three loads in flight; summed after the barrier
       if (KIND == kKindI8) {
-        for (int t = 0; t < p.n_taps; ++t) {
+        const int r0 = my_row + p.tap_off[0];
+        if (r0 >= 0 && r0 < p.M) rs = __ldg(p.a_rowsum + r0);
+        if (p.n_taps > 1) {
+          const int r1 = my_row + p.tap_off[1];
+          if (r1 >= 0 && r1 < p.M) rs1 = __ldg(p.a_rowsum + r1);
+        }
+        if (p.n_taps > 2) {
+          const int r2 = my_row + p.tap_off[2];
+          if (r2 >= 0 && r2 < p.M) rs2 = __ldg(p.a_rowsum + r2);
+        }
+        for (int t = 3; t < p.n_taps; ++t) {
           const int r = my_row + p.tap_off[t];
-          if (r >= 0 && r < p.M) rs += __ldg(p.a_rowsum + r);
+          if (r >= 0 && r < p.M) rs1 += __ldg(p.a_rowsum + r);
         }
       }
       const int pcol_param = n0 + et;                    // parameter arrays are padded to kTileN
@@ -508,7 +518,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         sp[2 * kTileN + et] = bno_v;
         reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = (KIND == kKindI8) ? kzz - zp_a * colsum_v : 0;
       }
-      if (KIND == kKindI8) rc.row_corr = p.zp_b * rs;
+      if (KIND == kKindI8) rc.row_corr = p.zp_b * (rs + rs1 + rs2);
       bool use_row = false;                              // takes part in the fused FindMinMax
       if (p.minmax) {
         int pos = my_row, P = p.M;
