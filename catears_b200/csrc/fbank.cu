@@ -247,13 +247,28 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
   const int64_t g0 = cd.sample_begin - shift;              // multiple of 8 samples
   const int n_vec = (shift + n_samples + 7) >> 3;
   const bool aligned = (reinterpret_cast<uintptr_t>(pcm) & 15) == 0;
-  for (int i = tid; i < n_vec; i += kThreads) {
-    int64_t g = g0 + 8 * (int64_t)i;
-    if (aligned && g + 8 <= total_samples) {
-      int4 q = __ldg(reinterpret_cast<const int4 *>(pcm + g));
-      *reinterpret_cast<int4 *>(xs + 8 * i) = q;
-    } else {
-      for (int j = 0; j < 8; ++j) xs[8 * i + j] = (g + j < total_samples) ? pcm[g + j] : (int16_t)0;
+  {
+    // every 16-byte load of this thread is issued before the first one is stored
+    constexpr int kVecPerThread = (kXsLen / 8 + kThreads) / kThreads;
+    int4 q[kVecPerThread];
+    bool fast[kVecPerThread];
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const int i = tid + k * kThreads;
+      const int64_t g = g0 + 8 * (int64_t)i;
+      fast[k] = i < n_vec && aligned && g + 8 <= total_samples;
+      q[k] = fast[k] ? __ldg(reinterpret_cast<const int4 *>(pcm + g)) : make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kVecPerThread; ++k) {
+      const int i = tid + k * kThreads;
+      if (i >= n_vec) continue;
+      if (fast[k]) {
+        *reinterpret_cast<int4 *>(xs + 8 * i) = q[k];
+      } else {
+        const int64_t g = g0 + 8 * (int64_t)i;
+        for (int j = 0; j < 8; ++j) xs[8 * i + j] = (g + j < total_samples) ? pcm[g + j] : (int16_t)0;
+      }
     }
   }
   for (int i = tid; i < kFrameLen; i += kThreads) s_ham[i] = tab->hamming[i];
