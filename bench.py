@@ -347,6 +347,21 @@ def run_gpu(args):
         ms_ll = timed(step_ll, max(1, args.steps // 2))
         e2e_ll = audio_per_step * max(1, args.steps // 2) / (ms_ll * 1e-3)
 
+    # The same with the k best (loglik, pdf) pairs per frame instead of the dense row (SURVEY 8f
+    # rank 4): 8 k bytes a frame over PCIe instead of 4 num_pdfs.
+    e2e_topk = None
+    if args.e2e_topk > 0 and world == 1:
+        k = args.e2e_topk
+        h_best = torch.empty((frames, 2 * k), dtype=torch.float32).pin_memory()
+        model.set_output("topk", k=k)
+
+        def step_topk():
+            model.forward(h_pcm.numpy(), off, loglik=h_best.numpy(), argmax=h_am.numpy(), stream=stream)
+        step_topk()
+        ms_topk = timed(step_topk, max(1, args.steps // 2))
+        e2e_topk = audio_per_step * max(1, args.steps // 2) / (ms_topk * 1e-3)
+        model.set_output("dense")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -418,6 +433,9 @@ def run_gpu(args):
     if e2e_ll is not None:
         out["e2e_loglik"] = {"value": round(e2e_ll, 1), "unit": UNIT,
                              "d2h_bytes_per_step": int(frames * (4 + 4 * model.num_pdfs))}
+    if e2e_topk is not None:
+        out["e2e_topk"] = {"value": round(e2e_topk, 1), "unit": UNIT, "k": args.e2e_topk,
+                           "d2h_bytes_per_step": int(frames * (4 + 8 * args.e2e_topk))}
     if base is not None:
         out["cpu_baseline"] = base
     print(json.dumps(out))
@@ -596,6 +614,8 @@ def main():
     ap.add_argument("--utts-per-gpu", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-loglik", action="store_true")
+    ap.add_argument("--e2e-topk", type=int, default=0,
+                    help="also time e2e with the k best (loglik, pdf) pairs per frame copied to the host")
     ap.add_argument("--workload", default="pipeline", choices=["pipeline", "frontend", "longform"],
                     help="pipeline = the headline fbank+CMVN+AM step (default); frontend = config 2; "
                          "longform = config 5 (one hour in time shards)")

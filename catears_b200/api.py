@@ -26,8 +26,12 @@ EXPORTS = [
     "ce_gpu_nnet_keep_acc", "ce_gpu_nnet_get_acc", "ce_gpu_quantize", "ce_gpu_gemm_u8",
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
     "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer", "ce_gpu_cmvn_stream",
-    "ce_gpu_partition", "ce_gpu_time_shards",
+    "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
+    "ce_gpu_model_output_width",
 ]
+OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
+# ce_gpu_scored_pdf_t: one entry of a top-k row
+SCORED_PDF = np.dtype([("loglik", np.float32), ("pdf", np.int32)])
 PROFILE_CATEGORIES = ["fbank", "cmvn", "gemm", "quantize", "finalize", "other"]
 
 
@@ -65,6 +69,8 @@ def lib():
     L.ce_gpu_nnet.argtypes = [vp, vp, i64p, C.c_int, vp, vp, vp]
     L.ce_gpu_forward.argtypes = [vp, vp, i64p, C.c_int, vp, vp, i64p, vp]
     L.ce_gpu_nnet_keep_acc.argtypes = [vp, C.c_int]
+    L.ce_gpu_model_set_output.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
+    L.ce_gpu_model_output_width.argtypes = [vp]
     L.ce_gpu_nnet_get_acc.argtypes = [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ce_gpu_quantize.argtypes = [vp, C.c_int64, C.c_int, vp, C.POINTER(C.c_float),
                                   C.POINTER(C.c_int32), C.c_int, vp]
@@ -301,9 +307,27 @@ class AcousticModelGpu:
 
     __del__ = close
 
+    def set_output(self, mode="dense", pdf_ids=None, k=0):
+        """What a row of `loglik` is from now on (ce_gpu_model_set_output): all pdfs, the columns
+        `pdf_ids`, or the `k` best as SCORED_PDF entries."""
+        ids, n = None, int(k)
+        if mode == "subset":
+            ids = np.ascontiguousarray(pdf_ids, np.int32)
+            n = ids.size
+        _check(lib().ce_gpu_model_set_output(
+            self._h, OUTPUT_MODES[mode], ids.ctypes.data_as(C.POINTER(C.c_int32)) if ids is not None else None,
+            n), "ce_gpu_model_set_output")
+        self._out_mode = mode
+
+    def output_width(self):
+        return lib().ce_gpu_model_output_width(self._h)
+
     def _outputs(self, n_frames, want_loglik, want_argmax, loglik, argmax):
         if loglik is None and want_loglik:
-            loglik = np.zeros((n_frames, self.num_pdfs), np.float32)
+            if getattr(self, "_out_mode", "dense") == "topk":
+                loglik = np.zeros((n_frames, self.output_width() // 2), SCORED_PDF)
+            else:
+                loglik = np.zeros((n_frames, self.output_width()), np.float32)
         if argmax is None and want_argmax:
             argmax = np.zeros(n_frames, np.int32)
         return loglik, argmax

@@ -382,6 +382,62 @@ int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sam
                     argmax, s);
 }
 
+int ce_gpu_model_set_output(ce_gpu_model_t *m, int mode, const int32_t *pdf_ids, int n) {
+  if (!m) {
+    SetError("ce_gpu_model_set_output: null model");
+    return CE_GPU_EINVAL;
+  }
+  const int NP = m->prog.num_pdfs;
+  if (mode == CE_GPU_OUTPUT_DENSE) {
+    m->out_sel = ce::OutSel();
+    return CE_GPU_OK;
+  }
+  if (mode != CE_GPU_OUTPUT_SUBSET && mode != CE_GPU_OUTPUT_TOPK) {
+    SetError("ce_gpu_model_set_output: unknown mode %d", mode);
+    return CE_GPU_EINVAL;
+  }
+  if (NP % 4 != 0 || NP > 4096) {
+    SetError("ce_gpu_model_set_output: a selected output needs num_pdfs %% 4 == 0 and <= 4096 (have %d)", NP);
+    return CE_GPU_EUNSUPPORTED;
+  }
+  if (mode == CE_GPU_OUTPUT_TOPK) {
+    if (n < 1 || n > NP || n > ce::kMaxTopK) {
+      SetError("ce_gpu_model_set_output: top-k needs 1 <= k <= min(num_pdfs, %d), got %d", ce::kMaxTopK, n);
+      return CE_GPU_EINVAL;
+    }
+    m->out_sel.mode = ce::kOutTopK;
+    m->out_sel.n = n;
+    m->out_sel.ids = nullptr;
+    return CE_GPU_OK;
+  }
+  if (!pdf_ids || n < 1) {
+    SetError("ce_gpu_model_set_output: empty pdf subset");
+    return CE_GPU_EINVAL;
+  }
+  for (int j = 0; j < n; ++j) {
+    if (pdf_ids[j] < 0 || pdf_ids[j] >= NP) {
+      SetError("ce_gpu_model_set_output: pdf_ids[%d] = %d is outside [0, %d)", j, pdf_ids[j], NP);
+      return CE_GPU_EINVAL;
+    }
+  }
+  CE_CHECK(UseDevice(m->device));
+  CE_CUDA(cudaDeviceSynchronize());                      // no earlier call still reads the old list
+  CE_CHECK(m->out_ids.Reserve(sizeof(int32_t) * (size_t)n));
+  CE_CUDA(cudaMemcpy(m->out_ids.ptr, pdf_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  m->out_sel.mode = ce::kOutSubset;
+  m->out_sel.n = n;
+  m->out_sel.ids = m->out_ids.as<int32_t>();
+  return CE_GPU_OK;
+}
+
+int ce_gpu_model_output_width(const ce_gpu_model_t *m) {
+  if (!m) {
+    SetError("ce_gpu_model_output_width: null model");
+    return CE_GPU_EINVAL;
+  }
+  return m->out_words();
+}
+
 int ce_gpu_nnet_keep_acc(ce_gpu_model_t *m, int linear_ordinal) {
   if (!m || linear_ordinal >= (int)m->blocks.size()) {
     SetError("ce_gpu_nnet_keep_acc: bad model / layer ordinal");

@@ -36,7 +36,7 @@ ce_gpu_model::~ce_gpu_model() {
   for (auto &b : blocks) {
     b.w[0].Free(); b.w[1].Free(); b.bias.Free(); b.bn_scale.Free(); b.bn_offset.Free(); b.colsum.Free();
   }
-  log_prior.Free(); cmvn_dev.Free();
+  log_prior.Free(); cmvn_dev.Free(); out_ids.Free();
   stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
   stage_argmax_all.Free();
   ws[0].Free(); ws[1].Free();
@@ -454,7 +454,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
 
   CE_CHECK(FinalizeLaunch(w->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
                           w->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
-                          m->log_prior.as<float>(), loglik_dev, NP, argmax_dev, s));
+                          m->log_prior.as<float>(), loglik_dev, m->out_words(), argmax_dev, s,
+                          m->out_sel));
   return CE_GPU_OK;
 }
 
@@ -467,7 +468,8 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     SetError("the model was loaded without CMVN statistics");
     return CE_GPU_EINVAL;
   }
-  const int L = m->left, R = m->right, NP = m->prog.num_pdfs;
+  const int L = m->left, R = m->right;
+  const int W = m->out_words();                          // 4-byte words per output row
   const bool ll_host = loglik && !IsDevicePtr(loglik);
   const bool am_host = argmax && !IsDevicePtr(argmax);
   const bool overlap = m->overlap && m->keep_acc < 0;
@@ -513,8 +515,8 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     ce::DevBuf *ll_stage = &m->ws[chunk & 1].stage_loglik;   // two staging buffers, alternating
     if (ll_host) {
       if (ll_pending[chunk & 1]) CE_CUDA(cudaStreamWaitEvent(cs, m->ll_copied[chunk & 1], 0));   // buffer free again
-      CE_CHECK(ll_stage->Reserve(sizeof(float) * (size_t)nf * NP));
-      ll_dev = ll_stage->as<float>() - f0 * NP;           // row f0 lands on the staging buffer's row 0
+      CE_CHECK(ll_stage->Reserve(sizeof(float) * (size_t)nf * W));
+      ll_dev = ll_stage->as<float>() - f0 * W;           // row f0 lands on the staging buffer's row 0
     }
     if (am_host) am_dev = m->stage_argmax_all.as<int32_t>() - frame_off[0];   // whole batch, one copy at the end
     PcmSource src = all;
@@ -535,7 +537,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     if (ll_host && nf > 0) {                               // off the compute stream: the next chunk starts now
       CE_CUDA(cudaEventRecord(m->ll_ready[chunk & 1], cs));
       CE_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ll_ready[chunk & 1], 0));
-      CE_CUDA(cudaMemcpyAsync(loglik + f0 * NP, ll_stage->ptr, sizeof(float) * (size_t)nf * NP,
+      CE_CUDA(cudaMemcpyAsync(loglik + f0 * W, ll_stage->ptr, sizeof(float) * (size_t)nf * W,
                               cudaMemcpyDeviceToHost, m->d2h_stream));
       CE_CUDA(cudaEventRecord(m->ll_copied[chunk & 1], m->d2h_stream));
       ll_pending[chunk & 1] = true;

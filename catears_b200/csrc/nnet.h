@@ -82,6 +82,15 @@ struct ce_gpu_model {
   std::vector<cudaEvent_t> copy_done;
   ce::DevBuf acc_dump;
 
+  // ---- what a log-likelihood row is written as (ce_gpu_model_set_output) ----
+  ce::OutSel out_sel;
+  ce::DevBuf out_ids;                  // the pdf subset on the device
+  // 4-byte words per output row: num_pdfs, the subset size, or 2 k
+  int out_words() const {
+    return out_sel.mode == ce::kOutDense ? prog.num_pdfs
+           : out_sel.mode == ce::kOutSubset ? out_sel.n : 2 * out_sel.n;
+  }
+
   // ---- debug: kept accumulators ----
   int keep_acc = -1;
   std::vector<int32_t> kept_row_off, kept_rows;   // per utterance of the last call
@@ -101,7 +110,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
 
 // feats_dev: [total_frames x feat_dim] fp32 on the device, utterance u = rows
 // [frame_off[u], frame_off[u+1]).  apply_cmvn: run the online CMVN with the model's global
-// stats while building the padded network input.  loglik [total_frames x num_pdfs] and
+// stats while building the padded network input.  loglik [total_frames x m->out_words()] and
 // argmax [total_frames] may each be nullptr, a device pointer, or a host pointer (host outputs
 // are copied back chunk by chunk and are complete on return).
 int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,

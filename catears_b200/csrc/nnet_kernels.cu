@@ -502,7 +502,320 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
   }
 }
 
-// Copies the valid rows [lo, P - hi) of one utterance out of a padded int32 matrix.
+// ---- selected output for the decoder feed ----------------------------
+// The decoder reads frame_logp(tid2pdf[ilabel]) for its active arcs only (src/decoder.cc:97-102),
+// while a dense row is 12 KB a frame over PCIe.  Both kernels below compute the row exactly like
+// finalize_rowcache_kernel (same operations, same order) and differ only in what they write.
+
+// The finished row of one warp: NV float4 per lane, column 4 (i 32 + lane) + q; padding = -FLT_MAX.
+template <int NV>
+__device__ __forceinline__ void FinalRow(const float *__restrict__ x, int N, int lane, int log_softmax,
+                                         const float *__restrict__ log_prior, float4 (&v)[NV]) {
+  const float4 *x4 = reinterpret_cast<const float4 *>(x);
+  const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
+  const int n4 = N >> 2;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < n4) ? __ldcs(x4 + c) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  }
+  float lse = 0.0f;
+  if (log_softmax) {
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) m = fmaxf(fmaxf(fmaxf(m, v[i].x), fmaxf(v[i].y, v[i].z)), v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float kLog2e = 1.4426950408889634f;
+    const float nm = -m * kLog2e;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < n4)
+        s += (Ex2(fmaf(v[i].x, kLog2e, nm)) + Ex2(fmaf(v[i].y, kLog2e, nm))) +
+             (Ex2(fmaf(v[i].z, kLog2e, nm)) + Ex2(fmaf(v[i].w, kLog2e, nm)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    lse = m + logf(s);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 32 + lane;
+    if (c < n4) {
+      const float4 lp = __ldg(lp4 + c);
+      float4 r = v[i];
+      if (log_softmax) {                                 // x -= log(sum)            vector.cc:120
+        r.x = __fsub_rn(r.x, lse); r.y = __fsub_rn(r.y, lse);
+        r.z = __fsub_rn(r.z, lse); r.w = __fsub_rn(r.w, lse);
+      }
+      r.x = __fsub_rn(r.x, lp.x); r.y = __fsub_rn(r.y, lp.y);   // AddVec(-1, log_prior_)  am.cc:111
+      r.z = __fsub_rn(r.z, lp.z); r.w = __fsub_rn(r.w, lp.w);
+      v[i] = r;
+    }
+  }
+}
+
+// Valid output row of padded row `row`, or -1.
+__device__ __forceinline__ int64_t OutputRowOf(int row, const int32_t *__restrict__ tile_utt,
+                                               const UttRows *__restrict__ utts,
+                                               const int64_t *__restrict__ out_row_off, int left,
+                                               int right) {
+  const int utt = tile_utt[row / kTileM];
+  const UttRows ur = utts[utt];
+  const int pos = row - ur.row_off;
+  if (pos < left || pos >= ur.rows - right) return -1;
+  return out_row_off[utt] + (pos - left);
+}
+
+// Subset: out[orow][j] = loglik[ids[j]], j < n_ids.  The row goes through shared memory (N floats
+// per warp) for the gather; the argmax is still the argmax over all N pdfs.
+template <int NV>
+__global__ void __launch_bounds__(128, 3)
+finalize_subset_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
+                       const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
+                       const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
+                       const float *__restrict__ log_prior, const int32_t *__restrict__ ids, int n_ids,
+                       float *__restrict__ out, int64_t ld_out, int32_t *__restrict__ argmax) {
+  extern __shared__ float4 s_rows4[];
+  const int lane = threadIdx.x & 31;
+  const int n4 = N >> 2;
+  float4 *srow4 = s_rows4 + (size_t)(threadIdx.x >> 5) * n4;
+  const float *srow = reinterpret_cast<const float *>(srow4);
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int rr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < M; rr += warps) {
+    const int row = M - 1 - rr;
+    const int64_t orow = OutputRowOf(row, tile_utt, utts, out_row_off, left, right);
+    if (orow < 0) continue;
+    float4 v[NV];
+    FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v);
+    float best = -FLT_MAX;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      if (c < n4) {
+        srow4[c] = v[i];
+        const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (e[q] > best) {
+            best = e[q];
+            best_i = 4 * c + q;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) {
+        best = ob;
+        best_i = oi;
+      }
+    }
+    if (argmax && lane == 0) argmax[orow] = best_i == 0x7fffffff ? 0 : best_i;
+    __syncwarp();
+    if (out) {
+      float *y = out + orow * ld_out;
+      for (int j = lane; j < n_ids; j += 32) __stcs(y + j, srow[__ldg(ids + j)]);
+    }
+    __syncwarp();                                        // the next row overwrites srow
+  }
+}
+
+// fp32 -> unsigned key with the same order (larger float, larger key), and back.
+__device__ __forceinline__ uint32_t OrderedKey(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float KeyToFloat(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// The k-th largest of the warp's 32 x LEN keys: the largest T with count(key >= T) >= k, found bit
+// by bit from the top (0 when fewer than k keys are non-zero).
+template <int LEN>
+__device__ __forceinline__ uint32_t WarpKthLargest(const uint32_t (&key)[LEN], int k) {
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < LEN; ++e) cnt += (key[e] >= cand) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, cnt) >= k) T = cand;
+  }
+  return T;
+}
+
+// Top-k: out[orow][j] = (loglik, pdf) of the j-th largest entry of the row, j < k; equal values in
+// ascending pdf order (so entry 0 is the argmax with "first maximum wins").  One warp per row, the
+// row's keys in registers.  The work is finding a lower bound T of the k-th largest key that leaves
+// few candidates, compacting the entries >= T into shared memory as 64-bit (inverted key : pdf)
+// words and sorting those (bitonic; ties order themselves by pdf):
+//   1. small k (MT > 0): every lane keeps its MT largest keys; the k-th largest of those 32 MT
+//      keys is such a bound, and a tight one while MT is about twice k / 32;
+//   2. otherwise, or when (1) leaves more than `cap` candidates: the k-th largest key bit by bit
+//      from the top over all keys, stopping as soon as at most `limit` candidates remain;
+//   3. rows where even the exact k-th largest key has more than `cap` entries at or above it (many
+//      equal values) compact exactly k entries: those above T and the lowest-numbered ties.
+template <int NV, int MT>
+__global__ void __launch_bounds__(128, 3)
+finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
+                     const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
+                     const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
+                     const float *__restrict__ log_prior, int k, int limit, int cap,
+                     uint2 *__restrict__ out, int64_t ld_out_pairs, int32_t *__restrict__ argmax) {
+  extern __shared__ unsigned long long s_list_all[];
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int n4 = N >> 2;
+  unsigned long long *list = s_list_all + (size_t)(threadIdx.x >> 5) * cap;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int rr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < M; rr += warps) {
+    const int row = M - 1 - rr;
+    const int64_t orow = OutputRowOf(row, tile_utt, utts, out_row_off, left, right);
+    if (orow < 0) continue;
+    uint32_t key[4 * NV];
+    {
+      float4 v[NV];
+      FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const bool in = i * 32 + lane < n4;              // padding sorts below every real entry
+        key[4 * i + 0] = in ? OrderedKey(v[i].x) : 0u;
+        key[4 * i + 1] = in ? OrderedKey(v[i].y) : 0u;
+        key[4 * i + 2] = in ? OrderedKey(v[i].z) : 0u;
+        key[4 * i + 3] = in ? OrderedKey(v[i].w) : 0u;
+      }
+    }
+    constexpr int kUnknown = 0x7fffffff;
+    uint32_t T = 0;
+    int n_cand = kUnknown;                               // count(key >= T)
+    if (MT > 0) {
+      uint32_t top[MT > 0 ? MT : 1];
+#pragma unroll
+      for (int j = 0; j < MT; ++j) top[j] = 0u;
+#pragma unroll
+      for (int e = 0; e < 4 * NV; ++e) {
+        uint32_t x = key[e];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {                    // top[] stays sorted, x sinks through it
+          const uint32_t hi = max(top[j], x);
+          x = min(top[j], x);
+          top[j] = hi;
+        }
+      }
+      const uint32_t L = WarpKthLargest<(MT > 0 ? MT : 1)>(top, k);
+      if (L != 0u) {
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < 4 * NV; ++e) c += (key[e] >= L) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c <= cap) {
+          T = L;
+          n_cand = c;
+        }
+      }
+    }
+    if (n_cand == kUnknown) {
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < 4 * NV; ++e) c += (key[e] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k) {
+          T = cand;
+          n_cand = c;
+          if (c <= limit) break;
+        }
+      }
+    }
+    int n_out = 0;
+    if (n_cand <= cap) {                                 // candidates: everything >= T
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const bool mine = key[4 * i] >= T || key[4 * i + 1] >= T || key[4 * i + 2] >= T || key[4 * i + 3] >= T;
+        if (!__any_sync(0xffffffffu, mine)) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t kk = key[4 * i + q];
+          const bool sel = kk >= T;
+          const uint32_t b = __ballot_sync(0xffffffffu, sel);
+          if (sel)
+            list[n_out + __popc(b & lt_mask)] =
+                ((unsigned long long)(~kk) << 32) | (uint32_t)(4 * (i * 32 + lane) + q);
+          n_out += __popc(b);
+        }
+      }
+    } else {                                             // T is exact here: above T, then the lowest ties
+      int n_gt = 0;
+#pragma unroll
+      for (int e = 0; e < 4 * NV; ++e) n_gt += (key[e] > T) ? 1 : 0;
+      const int need = k - __reduce_add_sync(0xffffffffu, n_gt);
+      int ties_seen = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const bool mine = key[4 * i] >= T || key[4 * i + 1] >= T || key[4 * i + 2] >= T || key[4 * i + 3] >= T;
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        // pdf order inside one i is (lane, q): ties in lower lanes come first, then my earlier q
+        int before = 0, total_eq = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t b_eq = __ballot_sync(0xffffffffu, key[4 * i + q] == T);
+          before += __popc(b_eq & lt_mask);
+          total_eq += __popc(b_eq);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t kk = key[4 * i + q];
+          bool sel = kk > T;
+          if (kk == T) {
+            sel = ties_seen + before < need;
+            ++before;
+          }
+          const uint32_t b = __ballot_sync(0xffffffffu, sel);
+          if (sel)
+            list[n_out + __popc(b & lt_mask)] =
+                ((unsigned long long)(~kk) << 32) | (uint32_t)(4 * (i * 32 + lane) + q);
+          n_out += __popc(b);
+        }
+        ties_seen += total_eq;
+      }
+    }
+    int n_sort = 1;                                      // n_out <= cap, a power of two
+    while (n_sort < n_out) n_sort <<= 1;
+    for (int j = n_out + lane; j < n_sort; j += 32) list[j] = ~0ull;
+    __syncwarp();
+    for (int size = 2; size <= n_sort; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < (n_sort >> 1); t += 32) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const unsigned long long a = list[lo], b = list[hi];
+          const bool up = (lo & size) == 0;
+          if ((a > b) == up) {
+            list[lo] = b;
+            list[hi] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (argmax && lane == 0) argmax[orow] = (int32_t)(uint32_t)list[0];
+    if (out) {
+      uint2 *y = out + orow * ld_out_pairs;
+      for (int j = lane; j < k; j += 32) {
+        const unsigned long long e = list[j];
+        __stcs(y + j, make_uint2(__float_as_uint(KeyToFloat(~(uint32_t)(e >> 32))), (uint32_t)e));
+      }
+    }
+    __syncwarp();                                        // the next row overwrites the list
+  }
+}
+
 }  // namespace
 
 int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s) {
@@ -585,13 +898,65 @@ int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
 int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
                    const UttRows *utts, const int64_t *out_row_off, int left, int right,
                    bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
-                   int32_t *argmax, cudaStream_t s) {
+                   int32_t *argmax, cudaStream_t s, const OutSel &sel) {
   if (M <= 0) return CE_GPU_OK;
   ProfScope prof(kProfFinalize, s);
+  const unsigned fgrid = (unsigned)std::min((M + 3) / 4, 32 * SmCount());
+  if (sel.mode != kOutDense) {
+    // the selecting kernels keep the row in registers: N % 4 == 0, N <= 4096 (checked when the
+    // selection is set, ce_gpu_model_set_output)
+    if (N % 4 != 0 || ld % 4 != 0 || N > 4096 || sel.n <= 0 ||
+        ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(log_prior)) & 15) != 0) {
+      SetError("FinalizeLaunch: output selection needs num_pdfs %% 4 == 0 and num_pdfs <= 4096");
+      return CE_GPU_EUNSUPPORTED;
+    }
+    // top-k: the candidates of one row sit in shared memory, `cap` entries per warp; the bit-by-bit
+    // search stops at `limit` candidates (about 1.5 k, a power of two: what the sort works on)
+    int limit = 32;
+    while (limit < sel.n + sel.n / 2) limit <<= 1;
+    const int cap = std::max(256, limit);
+    const size_t smem = sel.mode == kOutSubset ? sizeof(float) * 4 * (size_t)N
+                                               : sizeof(unsigned long long) * 4 * (size_t)cap;
+#define CE_FINALIZE_TOPK(NV, MT)                                                                  \
+  do {                                                                                            \
+    if (smem > 48 * 1024)                                                                         \
+      CE_CUDA(cudaFuncSetAttribute(finalize_topk_kernel<NV, MT>,                                  \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    finalize_topk_kernel<NV, MT><<<fgrid, 128, smem, s>>>(                                        \
+        logits, ld, N, M, tile_utt, utts, out_row_off, left, right, log_softmax ? 1 : 0,          \
+        log_prior, sel.n, limit, cap, reinterpret_cast<uint2 *>(loglik), ld_out / 2, argmax);     \
+  } while (0)
+#define CE_FINALIZE_SEL(NV)                                                                       \
+  do {                                                                                            \
+    if (sel.mode == kOutSubset) {                                                                 \
+      if (smem > 48 * 1024)                                                                       \
+        CE_CUDA(cudaFuncSetAttribute(finalize_subset_kernel<NV>,                                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      finalize_subset_kernel<NV><<<fgrid, 128, smem, s>>>(                                        \
+          logits, ld, N, M, tile_utt, utts, out_row_off, left, right, log_softmax ? 1 : 0,        \
+          log_prior, sel.ids, sel.n, loglik, ld_out, argmax);                                     \
+    } else if (sel.n <= 32) {                                                                     \
+      CE_FINALIZE_TOPK(NV, 2);                                                                    \
+    } else if (sel.n <= 64) {                                                                     \
+      CE_FINALIZE_TOPK(NV, 4);                                                                    \
+    } else if (sel.n <= 128) {                                                                    \
+      CE_FINALIZE_TOPK(NV, 8);                                                                    \
+    } else {                                                                                      \
+      CE_FINALIZE_TOPK(NV, 0);                                                                    \
+    }                                                                                             \
+  } while (0)
+    if (N <= 1024) CE_FINALIZE_SEL(8);
+    else if (N <= 2048) CE_FINALIZE_SEL(16);
+    else if (N <= 3072) CE_FINALIZE_SEL(24);
+    else CE_FINALIZE_SEL(32);
+#undef CE_FINALIZE_TOPK
+#undef CE_FINALIZE_SEL
+    CE_LAUNCHED();
+    return CE_GPU_OK;
+  }
   const bool vec = (N % 4 == 0) && (ld % 4 == 0) && (ld_out % 4 == 0) && N <= 4096 &&
                    ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(loglik) |
                      reinterpret_cast<uintptr_t>(log_prior)) & 15) == 0;
-  const unsigned fgrid = (unsigned)std::min((M + 3) / 4, 32 * SmCount());
 #define CE_FINALIZE(NV)                                                                            \
   finalize_rowcache_kernel<NV><<<fgrid, 128, 0, s>>>(logits, ld, N, M, tile_utt, utts,             \
                                                            out_row_off, left, right,               \

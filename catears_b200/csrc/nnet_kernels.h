@@ -30,10 +30,21 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
 int QuantSelfTestLaunch(int64_t n, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t s);
 int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
                   __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s);
+// What a finished log-likelihood row is written as (include/ce_gpu.h, ce_gpu_model_set_output):
+// all N columns, the columns ids[0..n) (device array), or the n best (loglik, pdf) pairs.
+enum { kOutDense = 0, kOutSubset = 1, kOutTopK = 2 };
+struct OutSel {
+  int mode = kOutDense;
+  int n = 0;
+  const int32_t *ids = nullptr;
+};
+// Largest n of a top-n selection (the sort runs in shared memory, 8 bytes an entry per warp).
+constexpr int kMaxTopK = 1024;
+// `loglik` rows are ld_out 4-byte words apart: N floats, n floats, or n (float, int32) pairs.
 int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
                    const UttRows *utts, const int64_t *out_row_off, int left, int right,
                    bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
-                   int32_t *argmax, cudaStream_t s);
+                   int32_t *argmax, cudaStream_t s, const OutSel &sel = OutSel());
 
 }  // namespace ce
 #endif  // CE_GPU_NNET_KERNELS_H_

@@ -124,7 +124,8 @@ int ce_gpu_rfft512(const float *in, int n_frames, float *out, int device, void *
 
 /* Acoustic model on ready features [total_frames x feat_dim]: per utterance replicate-pad,
  * propagate, subtract log prior.  loglik[total_frames x num_pdfs] (may be NULL if only argmax
- * is wanted); argmax[total_frames] int32 (may be NULL). */
+ * is wanted; see ce_gpu_model_set_output for narrower rows); argmax[total_frames] int32 (may be
+ * NULL). */
 int ce_gpu_nnet(ce_gpu_model_t *m, const float *feats, const int64_t *utt_frame_offsets,
                 int n_utts, float *loglik, int32_t *argmax, void *stream);
 
@@ -133,6 +134,33 @@ int ce_gpu_nnet(ce_gpu_model_t *m, const float *feats, const int64_t *utt_frame_
 int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sample_offsets,
                    int n_utts, float *loglik, int32_t *argmax,
                    int64_t *utt_frame_offsets_out, void *stream);
+
+/* ---- decoder feed: fewer bytes per frame (hazard H6) ----------------------
+ * A dense row is 4 num_pdfs bytes a frame (12 KB at 3072 pdfs), which caps a host decoder at what
+ * PCIe carries, while Decoder::Process only reads frame_logp(tid2pdf[ilabel]) of its active arcs
+ * (src/decoder.cc:97-102).  ce_gpu_model_set_output selects, for all later ce_gpu_nnet /
+ * ce_gpu_forward calls on the handle, what a row of `loglik` is:
+ *   CE_GPU_OUTPUT_DENSE   float[num_pdfs]                                   (the default)
+ *   CE_GPU_OUTPUT_SUBSET  float[n]: column j = log-likelihood of pdf pdf_ids[j] (HOST array, any
+ *                         order, repeats allowed).  Exact: give the decoder the matching remapped
+ *                         tid2pdf and it computes what it computed from the dense row.
+ *   CE_GPU_OUTPUT_TOPK    ce_gpu_scored_pdf_t[n]: the n largest log-likelihoods of the frame in
+ *                         descending order, equal values in ascending pdf order (pdf_ids unused);
+ *                         1 <= n <= min(num_pdfs, 1024).  What the host assumes for the pdfs not
+ *                         listed is its policy; entry n-1 bounds them from above.
+ * The values are those of the dense row, bit for bit; `argmax` is unaffected (always over all pdfs).
+ * Selected outputs need num_pdfs % 4 == 0 and num_pdfs <= 4096 (CE_GPU_EUNSUPPORTED otherwise).
+ * Not to be called while a forward call on the handle is in flight. */
+#define CE_GPU_OUTPUT_DENSE 0
+#define CE_GPU_OUTPUT_SUBSET 1
+#define CE_GPU_OUTPUT_TOPK 2
+typedef struct ce_gpu_scored_pdf {
+  float loglik;
+  int32_t pdf;
+} ce_gpu_scored_pdf_t;
+int ce_gpu_model_set_output(ce_gpu_model_t *m, int mode, const int32_t *pdf_ids, int n);
+/* 4-byte words per row of `loglik` under the current selection: num_pdfs, n, or 2 n. */
+int ce_gpu_model_output_width(const ce_gpu_model_t *m);
 
 /* Debug/parity hook (int8 models): after the next ce_gpu_nnet/ce_gpu_forward call the int32
  * accumulators of the `linear_ordinal`-th Linear layer are kept; fetch them with

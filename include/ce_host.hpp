@@ -237,8 +237,25 @@ class AcousticModel {
     ce_gpu_model_free(model_);
     model_ = ce_gpu_model_load_config(config_file.c_str(), precision, device);
     if (!model_) return Status::FromGpu(CE_GPU_EIO);
-    return Status::FromGpu(ce_gpu_model_info(model_, &num_pdfs_, &left_context_, &right_context_, &feat_dim_,
-                                             nullptr, nullptr));
+    st = Status::FromGpu(ce_gpu_model_info(model_, &num_pdfs_, &left_context_, &right_context_, &feat_dim_,
+                                           nullptr, nullptr));
+    out_width_ = num_pdfs_;
+    return st;
+  }
+
+  // What a row of log_prob is from now on (ce_gpu_model_set_output): every pdf
+  // (the reference's row), the listed pdfs only -- hand the decoder the matching remapped
+  // TransitionPdfIdMap and it computes the same costs --, or the k best as ce_gpu_scored_pdf_t
+  // pairs (two 4-byte words each; see ScoredRow).  Not while an Instance / Stream is mid-utterance.
+  Status SelectAllPdfs() { return SetOutput(CE_GPU_OUTPUT_DENSE, nullptr, 0); }
+  Status SelectPdfs(const std::vector<int32_t> &pdf_ids) {
+    return SetOutput(CE_GPU_OUTPUT_SUBSET, pdf_ids.data(), (int)pdf_ids.size());
+  }
+  Status SelectTopK(int k) { return SetOutput(CE_GPU_OUTPUT_TOPK, nullptr, k); }
+  // Columns (4-byte words) of every log_prob row under the current selection.
+  int output_width() const { return out_width_; }
+  static const ce_gpu_scored_pdf_t *ScoredRow(const Matrix &log_prob, int row) {
+    return reinterpret_cast<const ce_gpu_scored_pdf_t *>(log_prob.Row(row));
   }
 
   const std::vector<int32_t> &TransitionPdfIdMap() const { return tid2pdf_; }
@@ -297,16 +314,25 @@ class AcousticModel {
   Status ComputeBatch(Instance *inst, int batch_size, Matrix *log_prob) const {
     const int in_rows = batch_size + left_context_ + right_context_;
     const int64_t foff[2] = {0, in_rows};
-    scratch_.Resize(in_rows, num_pdfs_);
+    scratch_.Resize(in_rows, out_width_);
     int rc = ce_gpu_nnet(model_, inst->feats_buffer.data(), foff, 1, scratch_.data.data(), nullptr, nullptr);
     if (rc != CE_GPU_OK) return Status::FromGpu(rc);
-    log_prob->Resize(batch_size, num_pdfs_);
-    memcpy(log_prob->data.data(), scratch_.Row(left_context_), sizeof(float) * (size_t)batch_size * num_pdfs_);
+    log_prob->Resize(batch_size, out_width_);
+    memcpy(log_prob->data.data(), scratch_.Row(left_context_), sizeof(float) * (size_t)batch_size * out_width_);
+    return Status::OK();
+  }
+
+  Status SetOutput(int mode, const int32_t *ids, int n) {
+    if (!model_) return Status::RuntimeError("AcousticModel: output selection before Read");
+    int rc = ce_gpu_model_set_output(model_, mode, ids, n);
+    if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    out_width_ = ce_gpu_model_output_width(model_);
     return Status::OK();
   }
 
   ce_gpu_model_t *model_;
   int left_context_, right_context_, chunk_size_, num_pdfs_, feat_dim_;
+  int out_width_ = 0;
   std::vector<int32_t> tid2pdf_;
   mutable Matrix scratch_;
 };
@@ -346,7 +372,7 @@ class StreamBatch {
   Status Process(const std::vector<Stream *> &streams, const std::vector<const int16_t *> &pcm,
                  const std::vector<int> &n_samples, const std::vector<bool> &end_of_stream,
                  std::vector<Matrix> *rows) const {
-    const int n = (int)streams.size(), mel = am_->feat_dim(), P = am_->num_pdfs();
+    const int n = (int)streams.size(), mel = am_->feat_dim(), P = am_->output_width();
     const int L = am_->left_context(), R = am_->right_context();
     rows->assign(n, Matrix());
     // ---- 1. fbank of every stream's buffered samples, one call ----

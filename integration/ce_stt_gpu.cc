@@ -12,6 +12,14 @@
 // through ce_gpu_forward at ce_stt_end_of_stream (chunked and whole-utterance evaluation are the same
 // function), then the rows are fed to the unchanged Decoder::Process one by one, exactly
 // like src/ce_stt.cc:349-357.  The delta-LM rescoring option (src/ce_stt.cc:84-113) is not wired.
+//
+// CE_STT_GPU_OUTPUT selects what crosses PCIe per frame (ce_gpu_model_set_output):
+//   unset / "dense"  all num_pdfs log-likelihoods (12 KB a frame at 3072 pdfs);
+//   "subset"         only the pdfs the graph's input labels can reach; the decoder gets the
+//                    matching remapped transition-id map, so it computes exactly what it computed
+//                    from the dense row;
+//   "topk:<k>"       the k best (loglik, pdf) pairs; the row handed to the decoder holds those and
+//                    the k-th value (an upper bound) for every other pdf -- an approximation.
 #include "ce_stt.h"
 
 #include <stdio.h>
@@ -46,6 +54,13 @@ struct ce_stt_t {
   AcousticModel *am = nullptr;            // host copy: transition-id map and num_pdfs only
   SymbolTable *symbols = nullptr;
   ce_gpu_model_t *gpu = nullptr;          // the model that actually runs
+  // what a row of ce_gpu_forward's output is, and the transition-id map that goes with it
+  int out_mode = CE_GPU_OUTPUT_DENSE;
+  int top_k = 0;
+  Vector<int32_t> tid2col;                // subset mode: transition-id -> column of the gathered row
+  const Vector<int32_t> &DecoderMap() const {
+    return out_mode == CE_GPU_OUTPUT_SUBSET ? tid2col : am->TransitionPdfIdMap();
+  }
 };
 
 struct ce_utt_internal_t {
@@ -62,6 +77,29 @@ thread_local char g_error[2048] = "";     // ce_stt_last_error(): thread-local h
 void SetError(const std::string &msg) {
   strncpy(g_error, msg.c_str(), sizeof(g_error) - 1);
   g_error[sizeof(g_error) - 1] = '\0';
+}
+
+// Restricts the GPU output to the pdfs some arc of the graph can ask for (Decoder::LogLikelihood
+// reads frame_logp(tid2pdf[arc.ilabel]) and nothing else, src/decoder.cc:97-102,325-350).
+bool SelectGraphPdfs(ce_stt_t *r) {
+  const Vector<int32_t> &tid2pdf = r->am->TransitionPdfIdMap();
+  std::vector<int32_t> col_of(r->am->num_pdfs(), -1), ids;
+  r->tid2col.Resize(tid2pdf.Dim());
+  for (fst::StateIterator<fst::Fst<fst::StdArc>> si(*r->graph); !si.Done(); si.Next()) {
+    for (fst::ArcIterator<fst::Fst<fst::StdArc>> ai(*r->graph, si.Value()); !ai.Done(); ai.Next()) {
+      const int tid = ai.Value().ilabel;
+      if (tid == 0) continue;
+      if (tid < 0 || tid >= tid2pdf.Dim()) return false;
+      const int pdf = tid2pdf(tid);
+      if (col_of[pdf] < 0) {
+        col_of[pdf] = (int32_t)ids.size();
+        ids.push_back(pdf);
+      }
+      r->tid2col(tid) = col_of[pdf];
+    }
+  }
+  if (ids.empty()) return false;
+  return ce_gpu_model_set_output(r->gpu, CE_GPU_OUTPUT_SUBSET, ids.data(), (int)ids.size()) == CE_GPU_OK;
 }
 
 void StoreHyp(ce_utt_t *utt) {
@@ -110,6 +148,20 @@ ce_stt_t *ce_stt_init(const char *config_file) {
     r->gpu = ce_gpu_model_load_config(config_file, prec ? atoi(prec) : CE_GPU_PRECISION_FP32, 0);
     if (!r->gpu) st = Status::IOError(ce_gpu_last_error());
   }
+  if (st.ok()) {
+    const char *o = getenv("CE_STT_GPU_OUTPUT");
+    if (o && strcmp(o, "subset") == 0) {
+      r->out_mode = CE_GPU_OUTPUT_SUBSET;
+      if (!SelectGraphPdfs(r.get())) st = Status::Corruption(std::string("pdf subset: ") + ce_gpu_last_error());
+    } else if (o && strncmp(o, "topk:", 5) == 0) {
+      r->out_mode = CE_GPU_OUTPUT_TOPK;
+      r->top_k = atoi(o + 5);
+      if (ce_gpu_model_set_output(r->gpu, CE_GPU_OUTPUT_TOPK, nullptr, r->top_k) != CE_GPU_OK)
+        st = Status::Corruption(ce_gpu_last_error());
+    } else if (o && strcmp(o, "dense") != 0) {
+      st = Status::Corruption(std::string("CE_STT_GPU_OUTPUT: ") + o);
+    }
+  }
   if (!st.ok()) {
     SetError(st.what());
     ce_stt_destroy(r.release());
@@ -130,7 +182,7 @@ void ce_stt_destroy(ce_stt_t *r) {
 ce_utt_t *ce_utt_init(ce_stt_t *r, const ce_wave_format_t *format) {
   std::unique_ptr<ce_utt_internal_t> in(new ce_utt_internal_t());
   in->recognizer = r;
-  in->decoder.reset(new Decoder(r->graph, r->am->TransitionPdfIdMap(), 0.1f, nullptr));   // am_scale, src/ce_stt.cc:263
+  in->decoder.reset(new Decoder(r->graph, r->DecoderMap(), 0.1f, nullptr));   // am_scale, src/ce_stt.cc:263
   in->decoder->Initialize();
   Status st = in->wave_reader.SetFormat(*format);
   if (!st.ok()) {
@@ -181,14 +233,25 @@ void ce_stt_end_of_stream(ce_utt_t *utt) {
   int64_t foff[2] = {0, 0};
   const int64_t frames = ce_gpu_frame_offsets(soff, 1, foff);
   if (frames > 0) {
-    Matrix<float> log_prob((int)frames, in->recognizer->am->num_pdfs());
-    if (log_prob.Stride() != log_prob.NumCols() ||
-        ce_gpu_forward(in->recognizer->gpu, in->pcm.data(), soff, 1, log_prob.Data(), nullptr, nullptr,
-                       nullptr) != CE_GPU_OK) {
+    const ce_stt_t *rec = in->recognizer;
+    const int width = ce_gpu_model_output_width(rec->gpu);          // 4-byte words per row
+    std::vector<float> rows((size_t)frames * width);
+    if (ce_gpu_forward(rec->gpu, in->pcm.data(), soff, 1, rows.data(), nullptr, nullptr, nullptr) != CE_GPU_OK) {
       SetError(ce_gpu_last_error());
       return;
     }
-    for (int r = 0; r < log_prob.NumRows(); ++r) in->decoder->Process(log_prob.Row(r));
+    if (rec->out_mode == CE_GPU_OUTPUT_TOPK) {
+      Vector<float> dense(rec->am->num_pdfs());
+      for (int64_t r = 0; r < frames; ++r) {
+        const ce_gpu_scored_pdf_t *best = reinterpret_cast<const ce_gpu_scored_pdf_t *>(rows.data() + r * width);
+        for (int j = 0; j < dense.Dim(); ++j) dense(j) = best[rec->top_k - 1].loglik;
+        for (int j = 0; j < rec->top_k; ++j) dense(best[j].pdf) = best[j].loglik;
+        in->decoder->Process(dense);
+      }
+    } else {                                             // dense or gathered rows, as they are
+      for (int64_t r = 0; r < frames; ++r)
+        in->decoder->Process(pocketkaldi::SubVector<float>(rows.data() + r * width, width));
+    }
   }
   in->decoder->EndOfStream();
   StoreHyp(utt);

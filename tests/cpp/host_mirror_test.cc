@@ -131,6 +131,23 @@ static int Streams(int argc, char **argv) {
     st = detail::ReadVec0<float>(stats_path, &stats);
     if (!st.ok()) return Fail("cmvn stats", st);
   }
+  // HOST_MIRROR_SELECT = "subset:<id>,<id>,..." | "topk:<k>": narrower rows for the decoder
+  if (const char *sel = getenv("HOST_MIRROR_SELECT")) {
+    if (strncmp(sel, "topk:", 5) == 0) {
+      st = am.SelectTopK(atoi(sel + 5));
+    } else if (strncmp(sel, "subset:", 7) == 0) {
+      std::vector<int32_t> ids;
+      for (const char *p = sel + 7; *p;) {
+        char *end;
+        ids.push_back((int32_t)strtol(p, &end, 10));
+        p = (*end == ',') ? end + 1 : end;
+      }
+      st = am.SelectPdfs(ids);
+    } else {
+      st = Status::RuntimeError("HOST_MIRROR_SELECT");
+    }
+    if (!st.ok()) return Fail("output selection", st);
+  }
   const int n = argc - 7;
   std::vector<std::vector<int16_t>> audio(n);
   for (int i = 0; i < n; ++i) {
@@ -173,7 +190,7 @@ static int Streams(int argc, char **argv) {
     ++calls;
   }
   for (int i = 0; i < n; ++i) {
-    const int32_t hdr[3] = {(int32_t)(rows[i].size() / am.num_pdfs()), am.num_pdfs(), calls};
+    const int32_t hdr[3] = {(int32_t)(rows[i].size() / am.output_width()), am.output_width(), calls};
     FILE *o = fopen((prefix + "." + std::to_string(i) + ".bin").c_str(), "wb");
     if (!o) return Fail("open out", Status::IOError(prefix));
     fwrite(hdr, 4, 3, o);

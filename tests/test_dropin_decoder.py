@@ -118,3 +118,21 @@ def test_unchanged_decoder_on_gpu_loglikelihoods_matches_reference(setup):
         assert gpu.stdout == ref.stdout, (audio, ref.stdout, gpu.stdout)
     words = run(BIN_REF, setup["conf"], setup["wav"]).stdout.split()
     assert len(words) >= 20 and len(set(words)) >= 3              # a real path through the graph
+
+
+@pytest.mark.gpu
+def test_unchanged_decoder_on_selected_gpu_rows(setup):
+    """fewer bytes per frame to the host decoder.  The rows gathered to the pdfs
+    the graph can reach (with the remapped transition-id map) and the top-k rows with k = num_pdfs
+    decode to exactly the reference's words; a small k is an approximation that still decodes."""
+    for audio in (setup["wav"], setup["scp"]):
+        ref = run(BIN_REF, setup["conf"], audio)
+        assert ref.returncode == 0 and ref.stdout.strip() != ""
+        for sel in ("subset", "topk:96", "dense"):
+            gpu = run(BIN_GPU, setup["conf"], audio, env={"CE_STT_GPU_OUTPUT": sel})
+            assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+            assert gpu.stdout == ref.stdout, (sel, audio)
+    approx = run(BIN_GPU, setup["conf"], setup["wav"], env={"CE_STT_GPU_OUTPUT": "topk:24"})
+    assert approx.returncode == 0 and len(approx.stdout.split()) >= 20
+    bad = run(BIN_GPU, setup["conf"], setup["wav"], env={"CE_STT_GPU_OUTPUT": "topk:0"})
+    assert bad.returncode != 0

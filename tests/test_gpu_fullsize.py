@@ -41,6 +41,24 @@ def test_config3_full_batch_properties(tmp_path):
         l1, a1, _ = am.forward(pcm[u * 160000:(u + 1) * 160000])
         assert np.array_equal(l1, ll[u].cpu().numpy())
         assert np.array_equal(a1, d_am[u * 998:(u + 1) * 998].cpu().numpy())
+    # selected outputs at full width (3072 pdfs): the 64 best per frame and a
+    # 500-pdf subset of the first 64 utterances equal the dense rows' entries bit for bit
+    sub_off, n_sub = off[:65], 64 * 998
+    want_v, want_i = torch.sort(d_ll[:n_sub], dim=1, descending=True, stable=True)
+    for k in (64, 200, 300):                                 # the three code paths of the kernel
+        am.set_output("topk", k=k)
+        d_best = torch.empty((n_sub, 2 * k), dtype=torch.float32, device="cuda")
+        am.forward(d_pcm[:64 * 160000], sub_off, loglik=d_best, want_argmax=False)
+        torch.cuda.synchronize()
+        got = d_best.view(n_sub, k, 2)
+        assert bool(torch.equal(got[:, :, 0], want_v[:, :k])), k
+        assert bool(torch.equal(got[:, :, 1].contiguous().view(torch.int32), want_i[:, :k].int())), k
+    ids = np.random.default_rng(8).permutation(am.num_pdfs)[:500].astype(np.int32)
+    am.set_output("subset", pdf_ids=ids)
+    d_sub = torch.empty((n_sub, 500), dtype=torch.float32, device="cuda")
+    am.forward(d_pcm[:64 * 160000], sub_off, loglik=d_sub, want_argmax=False)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(d_sub, d_ll[:n_sub][:, torch.from_numpy(ids).long().cuda()]))
     am.close()
 
 

@@ -128,6 +128,41 @@ def test_stream_batch_micro_batches_equal_whole_utterances(exe, tmp_path, golden
 
 
 @pytest.mark.gpu
+def test_stream_batch_with_selected_outputs(exe, tmp_path, golden):
+    """SURVEY 8f rank 4 through the serving form: the same micro-batched streams with rows gathered
+    to a pdf subset, and with the 8 best (loglik, pdf) pairs per frame."""
+    m = synth.write_model(str(tmp_path / "m"), name="small", hidden=64, num_pdfs=96, seed=4321)
+    pcms, paths = [], []
+    for i, n in enumerate([8000, 47001, 64000]):
+        pcms.append(synth.synth_utterance(60 + i, n))
+        paths.append(str(tmp_path / ("s%d.s16le" % i)))
+        pcms[-1].astype("<i2").tofile(paths[-1])
+    prefix = str(tmp_path / "rows")
+    am = api.AcousticModelGpu(config=m["conf"], precision="fp32")
+    whole = [am.forward(p)[0] for p in pcms]
+    am.close()
+    ids = [90, 3, 4, 41, 3]
+    for sel in ("subset:" + ",".join(map(str, ids)), "topk:8"):
+        env = dict(os.environ, HOST_MIRROR_SELECT=sel)
+        r = subprocess.run([exe, "streams", m["conf"], str(api.PRECISION_FP32), "-", "3", prefix] + paths,
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        for i, w in enumerate(whole):
+            raw = np.fromfile("%s.%d.bin" % (prefix, i), np.int32, 3)
+            got = np.fromfile("%s.%d.bin" % (prefix, i), np.float32, offset=12).reshape(int(raw[0]), int(raw[1]))
+            assert got.shape[0] == w.shape[0]
+            if sel.startswith("subset"):
+                assert got.shape[1] == len(ids)
+                assert np.abs(got - w[:, ids]).max() < 1e-5
+            else:
+                best = got.view(api.SCORED_PDF)
+                assert best.shape == (w.shape[0], 8)
+                assert np.abs(best["loglik"] - np.sort(w, axis=1)[:, ::-1][:, :8]).max() < 1e-5
+                assert np.abs(best["loglik"] - np.take_along_axis(w, best["pdf"], axis=1)).max() < 1e-5
+                assert (np.diff(best["loglik"], axis=1) <= 0).all()
+
+
+@pytest.mark.gpu
 def test_cmvn_stream_is_bit_identical_for_any_split(golden):
     """ce_gpu_cmvn_stream: 1500 frames normalised in pieces of every size (1 .. 700 frames), two
     utterances at once, equal bit for bit to one ce_gpu_cmvn call."""
