@@ -692,7 +692,8 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
     }
     constexpr int kUnknown = 0x7fffffff;
     uint32_t T = 0;
-    int n_cand = kUnknown;                               // count(key >= T)
+    int n_cand = kUnknown;                               // count(key >= T) in the row,
+    int my_cand = 0;                                     // and among this lane's keys
     if (MT > 0) {
       uint32_t top[MT > 0 ? MT : 1];
 #pragma unroll
@@ -712,10 +713,11 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
         int c = 0;
 #pragma unroll
         for (int e = 0; e < 4 * NV; ++e) c += (key[e] >= L) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c <= cap) {
+        const int total = __reduce_add_sync(0xffffffffu, c);
+        if (total <= cap) {
           T = L;
-          n_cand = c;
+          n_cand = total;
+          my_cand = c;
         }
       }
     }
@@ -725,29 +727,31 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
         int c = 0;
 #pragma unroll
         for (int e = 0; e < 4 * NV; ++e) c += (key[e] >= cand) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= k) {
+        const int total = __reduce_add_sync(0xffffffffu, c);
+        if (total >= k) {
           T = cand;
-          n_cand = c;
-          if (c <= limit) break;
+          n_cand = total;
+          my_cand = c;
+          if (total <= limit) break;
         }
       }
     }
     int n_out = 0;
-    if (n_cand <= cap) {                                 // candidates: everything >= T
+    if (n_cand <= cap) {                                 // candidates: everything >= T, in any order
+      int incl = my_cand;                                // every lane appends its own after the lower lanes'
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      unsigned long long *mine = list + (incl - my_cand);
+      n_out = n_cand;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const bool mine = key[4 * i] >= T || key[4 * i + 1] >= T || key[4 * i + 2] >= T || key[4 * i + 3] >= T;
-        if (!__any_sync(0xffffffffu, mine)) continue;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t kk = key[4 * i + q];
-          const bool sel = kk >= T;
-          const uint32_t b = __ballot_sync(0xffffffffu, sel);
-          if (sel)
-            list[n_out + __popc(b & lt_mask)] =
-                ((unsigned long long)(~kk) << 32) | (uint32_t)(4 * (i * 32 + lane) + q);
-          n_out += __popc(b);
+          if (kk >= T) *mine++ = ((unsigned long long)(~kk) << 32) | (uint32_t)(4 * (i * 32 + lane) + q);
         }
       }
     } else {                                             // T is exact here: above T, then the lowest ties
