@@ -44,7 +44,7 @@ def forward_longform(models, pcm, want_loglik=True):
     m0 = models[0]
     total = int(api.frame_offsets([0, pcm.shape[0]])[-1])
     kb, ke, fb, fe = api.time_shards(total, n, m0.left_context, m0.right_context, 600)
-    loglik = np.zeros((total, m0.num_pdfs), np.float32) if want_loglik else None
+    loglik = None                                  # rows as the handles write them (set_output)
     argmax = np.zeros(total, np.int32)
     for p, m in enumerate(models):
         if ke[p] <= kb[p]:
@@ -53,6 +53,8 @@ def forward_longform(models, pcm, want_loglik=True):
         ll, am, _ = m.forward(pcm[s0:s1], want_loglik=want_loglik)
         a, b = int(kb[p] - fb[p]), int(ke[p] - fb[p])
         if want_loglik:
+            if loglik is None:
+                loglik = np.zeros((total,) + ll.shape[1:], ll.dtype)
             loglik[kb[p]:ke[p]] = ll[a:b]
         argmax[kb[p]:ke[p]] = am[a:b]
     return loglik, argmax
