@@ -19,7 +19,7 @@ void ce_gpu_model::ChunkWs::Free() {
   x0.Free(); feats.Free(); fbank_chunks.Free();
   for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
   act_u8.Free(); rowsum.Free(); logits.Free(); minmax.Free(); qparams.Free();
-  stage_loglik.Free(); stage_argmax.Free();
+  stage_loglik.Free();
   cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
   if (stream) cudaStreamDestroy(stream);
   if (stream_hi) cudaStreamDestroy(stream_hi);

@@ -56,7 +56,7 @@ struct ce_gpu_model {
     ce::DevBuf x0;                     // padded fp32 input [M x feat_dim]
     ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits;
     ce::DevBuf minmax, qparams;
-    ce::DevBuf stage_loglik, stage_argmax;
+    ce::DevBuf stage_loglik;
     ce::Table cmvn_utts, utt_table, tile_table, outrow_table;
     // `stream` (low priority) carries the memory-bound kernels, `stream_hi` (high priority) the
     // GEMMs: whenever a GEMM is ready its CTAs are placed first and the other chunk's
