@@ -27,8 +27,9 @@ EXPORTS = [
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
     "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer", "ce_gpu_cmvn_stream",
     "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
-    "ce_gpu_model_output_width",
+    "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback",
 ]
+ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
 # ce_gpu_scored_pdf_t: one entry of a top-k row
 SCORED_PDF = np.dtype([("loglik", np.float32), ("pdf", np.int32)])
@@ -71,6 +72,7 @@ def lib():
     L.ce_gpu_nnet_keep_acc.argtypes = [vp, C.c_int]
     L.ce_gpu_model_set_output.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
     L.ce_gpu_model_output_width.argtypes = [vp]
+    L.ce_gpu_model_set_rows_callback.argtypes = [vp, ROWS_READY_FN, vp]
     L.ce_gpu_nnet_get_acc.argtypes = [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ce_gpu_quantize.argtypes = [vp, C.c_int64, C.c_int, vp, C.POINTER(C.c_float),
                                   C.POINTER(C.c_int32), C.c_int, vp]
@@ -318,6 +320,14 @@ class AcousticModelGpu:
             self._h, OUTPUT_MODES[mode], ids.ctypes.data_as(C.POINTER(C.c_int32)) if ids is not None else None,
             n), "ce_gpu_model_set_output")
         self._out_mode = mode
+
+    def set_rows_callback(self, fn):
+        """fn(first_utt, n_utts, first_frame, n_frames) is called per chunk as soon as its rows
+        are complete in the caller's host buffers (ce_gpu_model_set_rows_callback); None removes
+        it.  Runs on a CUDA runtime thread: no CUDA / ce_gpu calls inside."""
+        cb = ROWS_READY_FN(lambda _u, a, b, c, d: fn(a, b, c, d)) if fn is not None else ROWS_READY_FN(0)
+        _check(lib().ce_gpu_model_set_rows_callback(self._h, cb, None), "ce_gpu_model_set_rows_callback")
+        self._rows_cb = cb                                 # keep the trampoline alive
 
     def output_width(self):
         return lib().ce_gpu_model_output_width(self._h)

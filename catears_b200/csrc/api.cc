@@ -430,6 +430,16 @@ int ce_gpu_model_set_output(ce_gpu_model_t *m, int mode, const int32_t *pdf_ids,
   return CE_GPU_OK;
 }
 
+int ce_gpu_model_set_rows_callback(ce_gpu_model_t *m, ce_gpu_rows_ready_fn fn, void *user) {
+  if (!m) {
+    SetError("ce_gpu_model_set_rows_callback: null model");
+    return CE_GPU_EINVAL;
+  }
+  m->rows_cb = fn;
+  m->rows_cb_user = fn ? user : nullptr;
+  return CE_GPU_OK;
+}
+
 int ce_gpu_model_output_width(const ce_gpu_model_t *m) {
   if (!m) {
     SetError("ce_gpu_model_output_width: null model");

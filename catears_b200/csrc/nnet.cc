@@ -462,6 +462,19 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
 }  // namespace
 
 namespace {
+// One chunk's "rows ready" notification, run by the CUDA runtime's host-function thread.
+struct RowsReady {
+  void (*fn)(void *, int, int, int64_t, int64_t);
+  void *user;
+  int first_utt, n_utts;
+  int64_t first_frame, n_frames;
+};
+void CUDART_CB RowsReadyTrampoline(void *p) {
+  RowsReady *r = static_cast<RowsReady *>(p);
+  r->fn(r->user, r->first_utt, r->n_utts, r->first_frame, r->n_frames);
+  delete r;
+}
+
 int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
                int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
   if (apply_cmvn && !m->has_cmvn) {
@@ -534,11 +547,23 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
     }
     CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
                           overlap ? w->stream_hi : cs));
-    if (ll_host && nf > 0) {                               // off the compute stream: the next chunk starts now
+    if ((ll_host || m->rows_cb) && nf > 0) {               // off the compute stream: the next chunk starts now
       CE_CUDA(cudaEventRecord(m->ll_ready[chunk & 1], cs));
       CE_CUDA(cudaStreamWaitEvent(m->d2h_stream, m->ll_ready[chunk & 1], 0));
-      CE_CUDA(cudaMemcpyAsync(loglik + f0 * W, ll_stage->ptr, sizeof(float) * (size_t)nf * W,
-                              cudaMemcpyDeviceToHost, m->d2h_stream));
+      if (ll_host)
+        CE_CUDA(cudaMemcpyAsync(loglik + f0 * W, ll_stage->ptr, sizeof(float) * (size_t)nf * W,
+                                cudaMemcpyDeviceToHost, m->d2h_stream));
+      if (m->rows_cb) {                                    // the consumer may start on this chunk now
+        if (am_host)
+          CE_CUDA(cudaMemcpyAsync(argmax + f0, m->stage_argmax_all.as<int32_t>() + (f0 - frame_off[0]),
+                                  sizeof(int32_t) * (size_t)nf, cudaMemcpyDeviceToHost, m->d2h_stream));
+        RowsReady *note = new RowsReady{m->rows_cb, m->rows_cb_user, u0, u1 - u0, f0, nf};
+        cudaError_t e = cudaLaunchHostFunc(m->d2h_stream, RowsReadyTrampoline, note);
+        if (e != cudaSuccess) {
+          delete note;
+          CE_CUDA(e);
+        }
+      }
       CE_CUDA(cudaEventRecord(m->ll_copied[chunk & 1], m->d2h_stream));
       ll_pending[chunk & 1] = true;
     }
@@ -554,11 +579,12 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   }
   for (int i = 0; i < 2; ++i)
     if (ll_pending[i]) CE_CUDA(cudaStreamWaitEvent(s, m->ll_copied[i], 0));
-  if (am_host && total_frames > 0) {
+  if (am_host && total_frames > 0 && !m->rows_cb) {      // (with a callback it went out chunk by chunk)
     CE_CUDA(cudaMemcpyAsync(argmax + frame_off[0], m->stage_argmax_all.ptr, sizeof(int32_t) * (size_t)total_frames,
                             cudaMemcpyDeviceToHost, s));
   }
-  if (ll_host || am_host) CE_CUDA(cudaStreamSynchronize(s));   // host outputs are complete on return
+  // host outputs are complete, and every callback has returned, on return
+  if (ll_host || am_host || m->rows_cb) CE_CUDA(cudaStreamSynchronize(s));
   return CE_GPU_OK;
 }
 }  // namespace

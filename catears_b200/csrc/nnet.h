@@ -91,6 +91,10 @@ struct ce_gpu_model {
            : out_sel.mode == ce::kOutSubset ? out_sel.n : 2 * out_sel.n;
   }
 
+  // ---- per-chunk completion callback (ce_gpu_model_set_rows_callback) ----
+  void (*rows_cb)(void *, int, int, int64_t, int64_t) = nullptr;
+  void *rows_cb_user = nullptr;
+
   // ---- debug: kept accumulators ----
   int keep_acc = -1;
   std::vector<int32_t> kept_row_off, kept_rows;   // per utterance of the last call

@@ -162,6 +162,22 @@ int ce_gpu_model_set_output(ce_gpu_model_t *m, int mode, const int32_t *pdf_ids,
 /* 4-byte words per row of `loglik` under the current selection: num_pdfs, n, or 2 n. */
 int ce_gpu_model_output_width(const ce_gpu_model_t *m);
 
+/* Row ring: a batch above the chunk size (CE_GPU_CHUNK_ROWS activation rows,
+ * 128 ten-second utterances by default) is evaluated chunk by chunk, and with a HOST `loglik`
+ * buffer chunk c's rows leave over PCIe while chunk c+1 is computed.  With a callback set, `fn` is
+ * called once per chunk, in order, as soon as the rows [first_frame, first_frame + n_frames) of
+ * `loglik` (and of a host `argmax`) of utterances [first_utt, first_utt + n_utts) are complete in
+ * the caller's buffers (utterance indices and frame numbers as in the call's offset arrays) -- so a
+ * CPU decoder can consume chunk c while the GPU works on c+1.  It runs on a thread owned by the
+ * CUDA runtime: it must not call CUDA or ce_gpu_* functions and should hand the chunk to a worker
+ * and return (the GPU runs at most two chunks ahead of a callback that has not returned -- the
+ * ring has two slots); the forward call returns only after the last callback has returned.  With
+ * device output buffers the callback only reports that the chunk's kernels have finished.
+ * fn == NULL removes it. */
+typedef void (*ce_gpu_rows_ready_fn)(void *user, int first_utt, int n_utts, int64_t first_frame,
+                                     int64_t n_frames);
+int ce_gpu_model_set_rows_callback(ce_gpu_model_t *m, ce_gpu_rows_ready_fn fn, void *user);
+
 /* Debug/parity hook (int8 models): after the next ce_gpu_nnet/ce_gpu_forward call the int32
  * accumulators of the `linear_ordinal`-th Linear layer are kept; fetch them with
  * ce_gpu_nnet_get_acc.  Pass -1 to disable. */

@@ -155,3 +155,53 @@ def test_set_output_errors(small_model, tmp_path):
             m.set_output("topk", k=4)
     finally:
         m.close()
+
+
+def test_rows_callback_per_chunk_rows_complete(small_model, monkeypatch):
+    """Row ring: with a callback set, every chunk is announced in order as soon as ITS rows (and
+    argmax) are complete in the caller's host buffers -- checked inside the callback, while later
+    chunks are still being computed -- and the call returns after the last callback."""
+    monkeypatch.setenv("CE_GPU_CHUNK_ROWS", "256")           # 2 utterances of 1 s per chunk
+    pcm, soff = synth.synth_batch(9, n_samples=16000)
+    soff = np.concatenate([soff[:4], [soff[3] + 100], soff[4:]])   # utterance 3 has no frame, 4 is shorter
+    m = api.AcousticModelGpu(config=small_model["conf"], precision="int8")
+    try:
+        want, want_am, foff = m.forward(pcm, soff)
+        ll = np.full_like(want, np.nan)
+        am = np.full_like(want_am, -1)
+        seen = []
+
+        def ready(first_utt, n_utts, first_frame, n_frames):
+            rows = slice(first_frame, first_frame + n_frames)
+            seen.append((first_utt, n_utts, first_frame, n_frames,
+                         bool(np.array_equal(ll[rows], want[rows])), bool(np.array_equal(am[rows], want_am[rows])),
+                         bool(np.isnan(ll[first_frame + n_frames:]).all())))
+        m.set_rows_callback(ready)
+        m.forward(pcm, soff, loglik=ll, argmax=am)
+        assert len(seen) >= 4
+        assert all(s[4] and s[5] for s in seen)              # complete at callback time
+        assert any(s[6] for s in seen[:-1])                  # ... while later rows had not arrived yet
+        utts = [u for s in seen for u in range(s[0], s[0] + s[1])]
+        assert utts == list(range(10))                        # every utterance once, in order
+        assert sum(s[3] for s in seen) == int(foff[-1])
+        for s in seen:
+            assert s[2] == foff[s[0]] and s[3] == foff[s[0] + s[1]] - foff[s[0]]
+        assert np.array_equal(ll, want) and np.array_equal(am, want_am)
+        # top-k rows ride the same ring; a device buffer only gets the notifications
+        import torch
+        m.set_output("topk", k=4)
+        seen.clear()
+        best = np.zeros((want.shape[0], 4), api.SCORED_PDF)
+        m.set_rows_callback(lambda *a: seen.append(a))
+        m.forward(pcm, soff, loglik=best, want_argmax=False)
+        assert sum(a[3] for a in seen) == int(foff[-1]) and np.array_equal(best["pdf"][:, 0], want_am)
+        n = len(seen)
+        d_out = torch.zeros((want.shape[0], 8), dtype=torch.float32, device="cuda")
+        m.forward(torch.from_numpy(pcm).cuda(), soff, loglik=d_out, want_argmax=False)
+        assert len(seen) >= n + 1
+        n = len(seen)
+        m.set_rows_callback(None)
+        m.forward(pcm, soff, loglik=best, want_argmax=False)
+        assert len(seen) == n
+    finally:
+        m.close()
