@@ -506,6 +506,8 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
 // The decoder reads frame_logp(tid2pdf[ilabel]) for its active arcs only (src/decoder.cc:97-102),
 // while a dense row is 12 KB a frame over PCIe.  Both kernels below compute the row exactly like
 // finalize_rowcache_kernel (same operations, same order) and differ only in what they write.
+// (The dense kernel keeps its own fused subtract-and-store loop: built on FinalRow it measured
+// 2.30-2.47 ms instead of 2.18-2.24 ms per step, the stores starting later.)
 
 // The finished row of one warp: NV float4 per lane, column 4 (i 32 + lane) + q; padding = -FLT_MAX.
 template <int NV>

@@ -32,7 +32,9 @@ def main():
         cases = []
         for c in only.split(","):
             mode, n = c.split(":")
-            if mode == "topk":
+            if mode == "dense":
+                cases.append(("dense", {}, model.num_pdfs))
+            elif mode == "topk":
                 cases.append(("topk", {"k": int(n)}, 2 * int(n)))
             else:
                 cases.append(("subset", {"pdf_ids": np.sort(rng.permutation(model.num_pdfs)[:int(n)])}, int(n)))
