@@ -27,7 +27,8 @@ EXPORTS = [
     "ce_gpu_gemm_f32", "ce_gpu_launch_count", "ce_gpu_profile_enable", "ce_gpu_profile_read",
     "ce_gpu_profile_trace", "ce_gpu_selftest_quantizer", "ce_gpu_cmvn_stream",
     "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
-    "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback",
+    "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback", "ce_gpu_streams_create",
+    "ce_gpu_streams_free", "ce_gpu_streams_open", "ce_gpu_streams_rows_ready", "ce_gpu_streams_process",
 ]
 ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
@@ -73,6 +74,15 @@ def lib():
     L.ce_gpu_model_set_output.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
     L.ce_gpu_model_output_width.argtypes = [vp]
     L.ce_gpu_model_set_rows_callback.argtypes = [vp, ROWS_READY_FN, vp]
+    ip = C.POINTER(C.c_int)
+    L.ce_gpu_streams_create.restype = vp
+    L.ce_gpu_streams_create.argtypes = [vp, C.c_int]
+    L.ce_gpu_streams_free.argtypes = [vp]
+    L.ce_gpu_streams_open.argtypes = [vp]
+    L.ce_gpu_streams_rows_ready.restype = C.c_int64
+    L.ce_gpu_streams_rows_ready.argtypes = [vp, ip, C.c_int, ip, C.POINTER(C.c_ubyte)]
+    L.ce_gpu_streams_process.argtypes = [vp, ip, C.c_int, C.POINTER(vp), ip, C.POINTER(C.c_ubyte), vp,
+                                         C.c_int64, i64p, vp]
     L.ce_gpu_nnet_get_acc.argtypes = [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ce_gpu_quantize.argtypes = [vp, C.c_int64, C.c_int, vp, C.POINTER(C.c_float),
                                   C.POINTER(C.c_int32), C.c_int, vp]
@@ -377,3 +387,53 @@ class AcousticModelGpu:
         _check(lib().ce_gpu_nnet_get_acc(self._h, utt, acc.ctypes.data, acc.size, C.byref(r), C.byref(c)),
                "ce_gpu_nnet_get_acc")
         return acc
+
+
+class StreamSet:
+    """Live utterances with their state on the device (ce_gpu_streams_*)."""
+
+    def __init__(self, model, max_streams):
+        self._m = model                                    # keeps the model alive
+        self._h = lib().ce_gpu_streams_create(model._h, max_streams)
+        if not self._h:
+            raise CeGpuError("ce_gpu_streams_create failed: %s" % last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ce_gpu_streams_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def open(self):
+        slot = lib().ce_gpu_streams_open(self._h)
+        _check(min(slot, 0), "ce_gpu_streams_open")
+        return slot
+
+    def _args(self, slots, pieces, eos):
+        n = len(slots)
+        sl = (C.c_int * n)(*slots)
+        cnt = (C.c_int * n)(*[0 if p is None else int(p.size) for p in pieces])
+        e = (C.c_ubyte * n)(*[1 if x else 0 for x in eos])
+        return n, sl, cnt, e
+
+    def rows_ready(self, slots, pieces, eos):
+        n, sl, cnt, e = self._args(slots, pieces, eos)
+        r = lib().ce_gpu_streams_rows_ready(self._h, sl, n, cnt, e)
+        _check(min(int(r), 0), "ce_gpu_streams_rows_ready")
+        return int(r)
+
+    def process(self, slots, pieces, eos, rows_cap=None):
+        """pieces[i]: int16 array of new samples of slots[i] (or None).  Returns one row matrix per
+        slot (host)."""
+        n, sl, cnt, e = self._args(slots, pieces, eos)
+        keep = [None if p is None else np.ascontiguousarray(p, np.int16) for p in pieces]
+        ptrs = (C.c_void_p * n)(*[None if p is None or p.size == 0 else p.ctypes.data for p in keep])
+        cap = self.rows_ready(slots, pieces, eos) if rows_cap is None else rows_cap
+        w = self._m.output_width()
+        flat = np.zeros((max(cap, 1), w), np.float32)
+        off = np.zeros(n + 1, np.int64)
+        _check(lib().ce_gpu_streams_process(self._h, sl, n, ptrs, cnt, e, flat.ctypes.data, cap,
+                                            off.ctypes.data_as(C.POINTER(C.c_int64)), None),
+               "ce_gpu_streams_process")
+        return [flat[off[i]:off[i + 1]] for i in range(n)]

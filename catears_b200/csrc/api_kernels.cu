@@ -48,7 +48,36 @@ __global__ void rowsum_u8_kernel(const uint8_t *__restrict__ x, int rows, int ld
   if (lane == 0) out[row] = s;
 }
 
+// Batched small copies (the per-stream state shuffles of streams.cc): CTA b copies entry b.
+__global__ void __launch_bounds__(256) segcopy_kernel(const SegCopy *__restrict__ segs) {
+  const SegCopy sc = segs[blockIdx.x];
+  const uintptr_t a = reinterpret_cast<uintptr_t>(sc.src) | reinterpret_cast<uintptr_t>(sc.dst) | sc.bytes;
+  for (uint32_t r = 0; r < sc.repeat; ++r) {
+    char *dst = static_cast<char *>(sc.dst) + (size_t)r * sc.bytes;
+    if ((a & 15) == 0) {
+      const uint4 *s4 = static_cast<const uint4 *>(sc.src);
+      uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+      for (uint32_t i = threadIdx.x; i < sc.bytes / 16; i += blockDim.x) d4[i] = s4[i];
+    } else if ((a & 3) == 0) {
+      const uint32_t *s1 = static_cast<const uint32_t *>(sc.src);
+      uint32_t *d1 = reinterpret_cast<uint32_t *>(dst);
+      for (uint32_t i = threadIdx.x; i < sc.bytes / 4; i += blockDim.x) d1[i] = s1[i];
+    } else {
+      const uint16_t *s2 = static_cast<const uint16_t *>(sc.src);
+      uint16_t *d2 = reinterpret_cast<uint16_t *>(dst);
+      for (uint32_t i = threadIdx.x; i < sc.bytes / 2; i += blockDim.x) d2[i] = s2[i];
+    }
+  }
+}
+
 }  // namespace
+
+int SegCopyLaunch(const SegCopy *segs_dev, int n, cudaStream_t s) {
+  if (n <= 0) return CE_GPU_OK;
+  segcopy_kernel<<<n, 256, 0, s>>>(segs_dev);
+  CE_LAUNCHED();
+  return CE_GPU_OK;
+}
 
 template <typename T>
 int TransposePadLaunch(const T *src, int rows, int cols, T *dst, int ld_dst, cudaStream_t s) {

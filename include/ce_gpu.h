@@ -178,6 +178,35 @@ typedef void (*ce_gpu_rows_ready_fn)(void *user, int first_utt, int n_utts, int6
                                      int64_t n_frames);
 int ce_gpu_model_set_rows_callback(ce_gpu_model_t *m, ce_gpu_rows_ready_fn fn, void *user);
 
+/* ---- live utterances with their state on the device -----------------------
+ * The streaming form of ce_gpu_forward: what the reference keeps per utterance in Fbank::Instance
+ * (samples that do not fill a frame yet, src/fbank.cc:308-313), CMVN (running sums + the last 600
+ * raw frames, src/cmvn.cc:35-68) and AcousticModel::Instance (frames waiting for their right
+ * context, src/am.cc:115-142) lives in per-slot device buffers of a stream set.  One process call
+ * takes whatever PCM has arrived for any subset of the open slots and runs ONE fbank, ONE CMVN
+ * (if the model has statistics) and ONE acoustic-model pass for all of them; only the new samples
+ * go up, only the finished rows come down.  Rows come out as soon as their right context exists
+ * and equal the whole-utterance rows (the CMVN chain continues exactly).
+ *   create   a set of max_streams slots on model m (m must outlive the set)
+ *   open     a free slot for a new utterance: its id (>= 0) or a negative error
+ *   process  slots[i]: distinct open slots; pcm[i]: HOST pointer to n_samples[i] new samples (may
+ *            be 0 / NULL); end_of_stream[i] != 0 (array may be NULL): no more audio -- the right
+ *            context is replicated, the remaining rows come out and the slot is free again.
+ *            rows: HOST or DEVICE buffer of rows_cap rows of ce_gpu_model_output_width(m) words;
+ *            rows [row_offsets[i], row_offsets[i+1]) belong to slots[i] (row_offsets: HOST, n+1).
+ *            If more than rows_cap rows are ready the call fails before changing anything.
+ *   rows_ready  how many rows that process call would produce (from the counters alone).
+ * Calls on one set (and on its model) must not overlap in time and are ordered by `stream`. */
+typedef struct ce_gpu_streams ce_gpu_streams_t;
+ce_gpu_streams_t *ce_gpu_streams_create(ce_gpu_model_t *m, int max_streams);
+void ce_gpu_streams_free(ce_gpu_streams_t *s);
+int ce_gpu_streams_open(ce_gpu_streams_t *s);
+int64_t ce_gpu_streams_rows_ready(const ce_gpu_streams_t *s, const int *slots, int n,
+                                  const int *n_samples, const unsigned char *end_of_stream);
+int ce_gpu_streams_process(ce_gpu_streams_t *s, const int *slots, int n, const int16_t *const *pcm,
+                           const int *n_samples, const unsigned char *end_of_stream, float *rows,
+                           int64_t rows_cap, int64_t *row_offsets, void *stream);
+
 /* Debug/parity hook (int8 models): after the next ce_gpu_nnet/ce_gpu_forward call the int32
  * accumulators of the `linear_ordinal`-th Linear layer are kept; fetch them with
  * ce_gpu_nnet_get_acc.  Pass -1 to disable. */

@@ -475,5 +475,68 @@ class StreamBatch {
   int device_;
 };
 
+// ---------------------------------------------------------------------------------------------
+// DeviceStreamBatch: the same micro-batching with the per-stream state kept ON THE DEVICE
+// (ce_gpu_streams_*): the host holds a slot number per live utterance, only the new samples go up
+// and only the finished rows come down.  Same kernels on the same inputs as StreamBatch, so the
+// rows are identical bit for bit.  The CMVN statistics are the model's (`cmvn_stats` in its config).
+// ---------------------------------------------------------------------------------------------
+class DeviceStreamBatch {
+ public:
+  struct Stream {
+    int slot = -1;                   // -1: not opened yet (Process opens it)
+    bool ended = false;
+    int64_t rows_emitted = 0;
+  };
+
+  DeviceStreamBatch(const AcousticModel *am, int max_streams)
+      : am_(am), set_(ce_gpu_streams_create(am->handle(), max_streams)) {}
+  ~DeviceStreamBatch() { ce_gpu_streams_free(set_); }
+  DeviceStreamBatch(const DeviceStreamBatch &) = delete;
+  DeviceStreamBatch &operator=(const DeviceStreamBatch &) = delete;
+
+  Status Process(const std::vector<Stream *> &streams, const std::vector<const int16_t *> &pcm,
+                 const std::vector<int> &n_samples, const std::vector<bool> &end_of_stream,
+                 std::vector<Matrix> *rows) const {
+    if (!set_) return Status::FromGpu(CE_GPU_ENOMEM);
+    const int n = (int)streams.size(), W = am_->output_width();
+    rows->assign(n, Matrix());
+    std::vector<int> slots(n);
+    std::vector<unsigned char> eos(n);
+    for (int i = 0; i < n; ++i) {
+      if (streams[i]->ended) return Status::RuntimeError("DeviceStreamBatch: stream already ended");
+      if (streams[i]->slot < 0) {
+        const int id = ce_gpu_streams_open(set_);
+        if (id < 0) return Status::FromGpu(id);
+        streams[i]->slot = id;
+      }
+      slots[i] = streams[i]->slot;
+      eos[i] = end_of_stream[i] ? 1 : 0;
+    }
+    const int64_t ready = ce_gpu_streams_rows_ready(set_, slots.data(), n, n_samples.data(), eos.data());
+    if (ready < 0) return Status::FromGpu((int)ready);
+    std::vector<float> flat((size_t)ready * W);
+    std::vector<int64_t> off(n + 1, 0);
+    int rc = ce_gpu_streams_process(set_, slots.data(), n, pcm.data(), n_samples.data(), eos.data(), flat.data(),
+                                    ready, off.data(), nullptr);
+    if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    for (int i = 0; i < n; ++i) {
+      const int r = (int)(off[i + 1] - off[i]);
+      (*rows)[i].Resize(r, W);
+      if (r > 0) memcpy((*rows)[i].data.data(), flat.data() + (size_t)off[i] * W, sizeof(float) * (size_t)r * W);
+      streams[i]->rows_emitted += r;
+      if (end_of_stream[i]) {
+        streams[i]->ended = true;
+        streams[i]->slot = -1;
+      }
+    }
+    return Status::OK();
+  }
+
+ private:
+  const AcousticModel *am_;
+  ce_gpu_streams_t *set_;
+};
+
 }  // namespace ce_host
 #endif  // CE_HOST_HPP_

@@ -112,6 +112,56 @@ static int Stream(int argc, char **argv) {
   return 0;
 }
 
+// Feeds the utterances in random-sized pieces through one batcher until all have ended; writes
+// <prefix>.<i>.bin with the rows of stream i in the order they came out.
+template <typename Batch, typename Rng>
+static int RunStreams(const Batch &batch, const AcousticModel &am, const std::vector<std::vector<int16_t>> &audio,
+                      Rng &next, const std::string &prefix) {
+  const int n = (int)audio.size();
+  Status st;
+  std::vector<typename Batch::Stream> state(n);
+  std::vector<size_t> pos(n, 0);
+  std::vector<std::vector<float>> rows(n);
+  int calls = 0, live = n;
+  while (live > 0) {
+    std::vector<typename Batch::Stream *> streams;
+    std::vector<const int16_t *> pcm;
+    std::vector<int> cnt;
+    std::vector<bool> eos;
+    std::vector<int> idx;
+    for (int i = 0; i < n; ++i) {
+      if (state[i].ended) continue;
+      size_t take = next() % 3 == 0 ? 0 : next() % 9000;     // sometimes nothing arrives
+      take = std::min(take, audio[i].size() - pos[i]);
+      streams.push_back(&state[i]);
+      pcm.push_back(audio[i].data() + pos[i]);
+      cnt.push_back((int)take);
+      pos[i] += take;
+      eos.push_back(pos[i] == audio[i].size());
+      idx.push_back(i);
+    }
+    std::vector<Matrix> out;
+    st = batch.Process(streams, pcm, cnt, eos, &out);
+    if (!st.ok()) return Fail("StreamBatch::Process", st);
+    for (size_t k = 0; k < idx.size(); ++k) {
+      rows[idx[k]].insert(rows[idx[k]].end(), out[k].data.begin(), out[k].data.end());
+      if (state[idx[k]].ended) --live;
+    }
+    ++calls;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int32_t hdr[3] = {(int32_t)(rows[i].size() / am.output_width()), am.output_width(), calls};
+    FILE *o = fopen((prefix + "." + std::to_string(i) + ".bin").c_str(), "wb");
+    if (!o) return Fail("open out", Status::IOError(prefix));
+    fwrite(hdr, 4, 3, o);
+    fwrite(rows[i].data(), 4, rows[i].size(), o);
+    fclose(o);
+  }
+  printf("OK streams=%d calls=%d\n", n, calls);
+  return 0;
+}
+
+
 // streams <conf> <precision> <cmvn_stats.vec0 | -> <seed> <out_prefix> <pcm.s16le>...
 // Several live utterances fed in random-sized pieces through ONE StreamBatch; writes
 // <out_prefix>.<i>.bin with the rows of stream i in the order they came out.
@@ -158,47 +208,9 @@ static int Streams(int argc, char **argv) {
     while ((got = fread(buf, 2, 4096, f)) > 0) audio[i].insert(audio[i].end(), buf, buf + got);
     fclose(f);
   }
-  StreamBatch batch(&am, stats, 0);
-  std::vector<StreamBatch::Stream> state(n);
-  std::vector<size_t> pos(n, 0);
-  std::vector<std::vector<float>> rows(n);
-  int calls = 0, live = n;
-  while (live > 0) {
-    std::vector<StreamBatch::Stream *> streams;
-    std::vector<const int16_t *> pcm;
-    std::vector<int> cnt;
-    std::vector<bool> eos;
-    std::vector<int> idx;
-    for (int i = 0; i < n; ++i) {
-      if (state[i].ended) continue;
-      size_t take = next() % 3 == 0 ? 0 : next() % 9000;     // sometimes nothing arrives
-      take = std::min(take, audio[i].size() - pos[i]);
-      streams.push_back(&state[i]);
-      pcm.push_back(audio[i].data() + pos[i]);
-      cnt.push_back((int)take);
-      pos[i] += take;
-      eos.push_back(pos[i] == audio[i].size());
-      idx.push_back(i);
-    }
-    std::vector<Matrix> out;
-    st = batch.Process(streams, pcm, cnt, eos, &out);
-    if (!st.ok()) return Fail("StreamBatch::Process", st);
-    for (size_t k = 0; k < idx.size(); ++k) {
-      rows[idx[k]].insert(rows[idx[k]].end(), out[k].data.begin(), out[k].data.end());
-      if (state[idx[k]].ended) --live;
-    }
-    ++calls;
-  }
-  for (int i = 0; i < n; ++i) {
-    const int32_t hdr[3] = {(int32_t)(rows[i].size() / am.output_width()), am.output_width(), calls};
-    FILE *o = fopen((prefix + "." + std::to_string(i) + ".bin").c_str(), "wb");
-    if (!o) return Fail("open out", Status::IOError(prefix));
-    fwrite(hdr, 4, 3, o);
-    fwrite(rows[i].data(), 4, rows[i].size(), o);
-    fclose(o);
-  }
-  printf("OK streams=%d calls=%d\n", n, calls);
-  return 0;
+  if (getenv("HOST_MIRROR_DEVICE_STATE"))              // same schedule, state on the device
+    return RunStreams<DeviceStreamBatch>(DeviceStreamBatch(&am, n + 2), am, audio, next, prefix);
+  return RunStreams<StreamBatch>(StreamBatch(&am, stats, 0), am, audio, next, prefix);
 }
 
 int main(int argc, char **argv) {

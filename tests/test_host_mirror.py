@@ -163,6 +163,73 @@ def test_stream_batch_with_selected_outputs(exe, tmp_path, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec,select", [("fp32", None), ("int8", None), ("fp32", "topk:8")])
+def test_device_resident_streams_equal_host_resident_bit_for_bit(exe, tmp_path, golden, prec, select):
+    """ce_gpu_streams_* keeps the sample remainder, the CMVN sums + history and the AM context of
+    every live utterance in device buffers; fed with the same random schedule it must produce the
+    very rows of ce_host::StreamBatch (which carries that state on the host): same kernels, same
+    inputs."""
+    stats = golden["cmvn_stats"]
+    m = synth.write_model(str(tmp_path / "m"), name="small", hidden=64, num_pdfs=96, seed=4321, cmvn_stats=stats)
+    stats_path = str(tmp_path / "stats.vec0")
+    F.write_vector(stats_path, stats)
+    paths = []
+    for i, n in enumerate([8000, 192000, 300, 47001, 112345, 399, 400]):   # 12 s: the CMVN window slides
+        paths.append(str(tmp_path / ("s%d.s16le" % i)))
+        synth.synth_utterance(40 + i, n).astype("<i2").tofile(paths[-1])
+    out = {}
+    for mode in ("host", "device"):
+        env = dict(os.environ)
+        if mode == "device":
+            env["HOST_MIRROR_DEVICE_STATE"] = "1"
+        if select:
+            env["HOST_MIRROR_SELECT"] = select
+        prefix = str(tmp_path / ("rows_" + mode))
+        r = subprocess.run([exe, "streams", m["conf"], str(api.PRECISIONS[prec]), stats_path, "5", prefix] + paths,
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        out[mode] = [np.fromfile("%s.%d.bin" % (prefix, i), np.int32) for i in range(len(paths))]
+    for i, (a, b) in enumerate(zip(out["host"], out["device"])):
+        assert a[2] > 3 and np.array_equal(a, b), i            # header and every row bit
+    assert out["host"][1][0] == 1198 and out["host"][2][0] == 0 and out["host"][6][0] == 1
+
+
+@pytest.mark.gpu
+def test_stream_set_slot_reuse_and_row_capacity(tmp_path, golden):
+    """A slot that ended is free again and starts from nothing; a row buffer that is too small is
+    refused before any state changes."""
+    stats = golden["cmvn_stats"]
+    m = synth.write_model(str(tmp_path / "m"), name="small", hidden=64, num_pdfs=96, seed=4321, cmvn_stats=stats)
+    am = api.AcousticModelGpu(config=m["conf"], precision="fp32")
+    s = api.StreamSet(am, 2)
+    try:
+        a, b, c = (synth.synth_utterance(70 + i, n) for i, n in enumerate((30000, 52000, 41000)))
+        sa, sb = s.open(), s.open()
+        assert (sa, sb) == (0, 1)
+        with pytest.raises(api.CeGpuError):
+            s.open()                                         # both slots taken
+        got_a = [s.process([sa, sb], [a[:20000], b[:7000]], [False, False])]
+        assert s.rows_ready([sa], [a[20000:]], [True]) == 186 - got_a[0][0].shape[0]
+        with pytest.raises(api.CeGpuError, match="nothing was changed"):
+            s.process([sa], [a[20000:]], [True], rows_cap=3)
+        got_a.append(s.process([sa, sb], [a[20000:], b[7000:30000]], [True, False]))
+        sc = s.open()
+        assert sc == sa                                      # the ended slot is free again
+        got_c = s.process([sc, sb], [c, b[30000:]], [True, True])
+        rows_a = np.concatenate([got_a[0][0], got_a[1][0]])
+        rows_b = np.concatenate([got_a[0][1], got_a[1][1], got_c[1]])
+        for rows, pcm in ((rows_a, a), (rows_b, b), (got_c[0], c)):
+            whole, _, _ = am.forward(pcm)
+            assert rows.shape == whole.shape
+            assert np.abs(rows - whole).max() < 1e-5
+        with pytest.raises(api.CeGpuError):
+            s.process([sb], [None], [False])                 # ended: not open any more
+    finally:
+        s.close()
+        am.close()
+
+
+@pytest.mark.gpu
 def test_cmvn_stream_is_bit_identical_for_any_split(golden):
     """ce_gpu_cmvn_stream: 1500 frames normalised in pieces of every size (1 .. 700 frames), two
     utterances at once, equal bit for bit to one ce_gpu_cmvn call."""
