@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -112,6 +113,21 @@ static int Stream(int argc, char **argv) {
   return 0;
 }
 
+// HOST_MIRROR_SELECT = "subset:<id>,<id>,..." | "topk:<k>": narrower rows for the decoder
+static Status SelectFromEnv(AcousticModel *am) {
+  const char *sel = getenv("HOST_MIRROR_SELECT");
+  if (!sel) return Status::OK();
+  if (strncmp(sel, "topk:", 5) == 0) return am->SelectTopK(atoi(sel + 5));
+  if (strncmp(sel, "subset:", 7) != 0) return Status::RuntimeError("HOST_MIRROR_SELECT");
+  std::vector<int32_t> ids;
+  for (const char *p = sel + 7; *p;) {
+    char *end;
+    ids.push_back((int32_t)strtol(p, &end, 10));
+    p = (*end == ',') ? end + 1 : end;
+  }
+  return am->SelectPdfs(ids);
+}
+
 // Feeds the utterances in random-sized pieces through one batcher until all have ended; writes
 // <prefix>.<i>.bin with the rows of stream i in the order they came out.
 template <typename Batch, typename Rng>
@@ -181,23 +197,8 @@ static int Streams(int argc, char **argv) {
     st = detail::ReadVec0<float>(stats_path, &stats);
     if (!st.ok()) return Fail("cmvn stats", st);
   }
-  // HOST_MIRROR_SELECT = "subset:<id>,<id>,..." | "topk:<k>": narrower rows for the decoder
-  if (const char *sel = getenv("HOST_MIRROR_SELECT")) {
-    if (strncmp(sel, "topk:", 5) == 0) {
-      st = am.SelectTopK(atoi(sel + 5));
-    } else if (strncmp(sel, "subset:", 7) == 0) {
-      std::vector<int32_t> ids;
-      for (const char *p = sel + 7; *p;) {
-        char *end;
-        ids.push_back((int32_t)strtol(p, &end, 10));
-        p = (*end == ',') ? end + 1 : end;
-      }
-      st = am.SelectPdfs(ids);
-    } else {
-      st = Status::RuntimeError("HOST_MIRROR_SELECT");
-    }
-    if (!st.ok()) return Fail("output selection", st);
-  }
+  st = SelectFromEnv(&am);
+  if (!st.ok()) return Fail("output selection", st);
   const int n = argc - 7;
   std::vector<std::vector<int16_t>> audio(n);
   for (int i = 0; i < n; ++i) {
@@ -213,7 +214,63 @@ static int Streams(int argc, char **argv) {
   return RunStreams<StreamBatch>(StreamBatch(&am, stats, 0), am, audio, next, prefix);
 }
 
+// streambench <conf> <precision> <cmvn_stats.vec0 | -> <n_streams> <samples_per_call> <calls>
+// Serving-shaped timing: n live streams each receive samples_per_call new samples per call; wall
+// milliseconds per call for host-resident (StreamBatch) and device-resident (DeviceStreamBatch)
+// state.  Not a test: tools/stream_probe.py runs it.
+template <typename Batch>
+static double TimeCalls(const Batch &batch, int n, int per_call, int calls) {
+  std::vector<typename Batch::Stream> state(n);
+  std::vector<typename Batch::Stream *> streams;
+  std::vector<std::vector<int16_t>> audio(n, std::vector<int16_t>(per_call));
+  std::vector<const int16_t *> pcm;
+  uint32_t x = 12345;
+  for (int i = 0; i < n; ++i) {
+    for (int16_t &v : audio[i]) {
+      x = x * 1664525u + 1013904223u;
+      v = (int16_t)((int)(x >> 18) - 8192);
+    }
+    streams.push_back(&state[i]);
+    pcm.push_back(audio[i].data());
+  }
+  const std::vector<int> cnt(n, per_call);
+  const std::vector<bool> eos(n, false);
+  std::vector<Matrix> out;
+  double ms = 0.0;
+  for (int c = 0; c < calls + 3; ++c) {                     // 3 warm-up calls
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    Status st = batch.Process(streams, pcm, cnt, eos, &out);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (!st.ok()) return -1.0;
+    if (c >= 3) ms += 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec);
+  }
+  return ms / calls;
+}
+
+static int StreamBench(char **argv) {
+  const std::string conf = argv[2], stats_path = argv[4];
+  const int n = atoi(argv[5]), per_call = atoi(argv[6]), calls = atoi(argv[7]);
+  AcousticModel am;
+  Status st = am.Read(conf, atoi(argv[3]), 0);
+  if (!st.ok()) return Fail("AcousticModel::Read", st);
+  st = SelectFromEnv(&am);
+  if (!st.ok()) return Fail("output selection", st);
+  std::vector<float> stats;
+  if (stats_path != "-") {
+    st = detail::ReadVec0<float>(stats_path, &stats);
+    if (!st.ok()) return Fail("cmvn stats", st);
+  }
+  const double host_ms = TimeCalls(StreamBatch(&am, stats, 0), n, per_call, calls);
+  const double dev_ms = TimeCalls(DeviceStreamBatch(&am, n), n, per_call, calls);
+  if (host_ms < 0 || dev_ms < 0) return Fail("Process", Status::RuntimeError("streambench"));
+  printf("streams=%d samples_per_call=%d row_words=%d host_state_ms=%.3f device_state_ms=%.3f\n", n, per_call,
+         am.output_width(), host_ms, dev_ms);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 8 && strcmp(argv[1], "streambench") == 0) return StreamBench(argv);
   if (argc >= 2 && strcmp(argv[1], "errors") == 0) return Errors();
   if (argc >= 6 && strcmp(argv[1], "stream") == 0) return Stream(argc, argv);
   if (argc >= 8 && strcmp(argv[1], "streams") == 0) return Streams(argc, argv);
