@@ -37,7 +37,8 @@ constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quad
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
-constexpr int kParamBytes = 4 * kTileN * 4;              // bias, bn scale, bn offset, int correction
+constexpr int kParamBytes = 7 * kTileN * 4;              // bias, bn scale, bn offset, int correction (x4
+                                                         // in granule mode: one per 32-row quadrant)
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
 
@@ -252,11 +253,12 @@ struct RowConst {
 
 template <int KIND, bool RELU, bool BN, bool MM>
 __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[32], const float *sp,
-                                         int pcol, const RowConst rc, float &vmin, float &vmax) {
+                                         int corr_off, int pcol, const RowConst rc, float &vmin,
+                                         float &vmax) {
   const float4 *b4 = reinterpret_cast<const float4 *>(sp + pcol);
   const float4 *s4 = reinterpret_cast<const float4 *>(sp + kTileN + pcol);
   const float4 *o4 = reinterpret_cast<const float4 *>(sp + 2 * kTileN + pcol);
-  const int4 *c4 = reinterpret_cast<const int4 *>(sp + 3 * kTileN + pcol);
+  const int4 *c4 = reinterpret_cast<const int4 *>(sp + corr_off + pcol);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 bb = b4[q];
@@ -300,7 +302,7 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
 // ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
-template <int KIND, int CG>
+template <int KIND, int CG, bool GRAN = false>
 __global__ void __maxnreg__(128)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
@@ -468,7 +470,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t tempty0 = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
-    const int row_tiles = (p.M + kTileM - 1) / kTileM;
+    const int n_gran = (p.M + kRowGran - 1) / kRowGran;
+    // granule mode: every 32-row quadrant of the tile may belong to another utterance, so the
+    // per-column integer correction (it contains the utterance's zero point) exists once per quadrant
+    const int corr_off = (3 + (GRAN ? quad : 0)) * kTileN;
     for (int tile = group_id; tile < total_tiles; tile += n_groups) {
       const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
       const int n0 = (tile % n_tiles) * kTileN;
@@ -499,7 +504,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const float bns_v = p.bn_scale ? __ldg(p.bn_scale + pcol_param) : 1.0f;
       const float bno_v = p.bn_offset ? __ldg(p.bn_offset + pcol_param) : 0.0f;
       const int32_t colsum_v = (KIND == kKindI8) ? __ldg(p.b_colsum + pcol_param) : 0;
-      const int utt = p.tile_utt ? p.tile_utt[min(m0 / kTileM, row_tiles - 1)] : 0;
+      const int utt = p.tile_utt ? p.tile_utt[min(m0 / kRowGran + (GRAN ? quad : 0), n_gran - 1)] : 0;
       int32_t zp_a = 0;
       RowConst rc;
       rc.row_corr = 0;
@@ -516,7 +521,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         sp[et] = bias_v;
         sp[kTileN + et] = bns_v;
         sp[2 * kTileN + et] = bno_v;
-        reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = (KIND == kKindI8) ? kzz - zp_a * colsum_v : 0;
+        if (!GRAN) {
+          reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = (KIND == kKindI8) ? kzz - zp_a * colsum_v : 0;
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int32_t zg = p.qa[p.tile_utt[min(m0 / kRowGran + g, n_gran - 1)]].zero_point;
+            reinterpret_cast<int32_t *>(sp)[(3 + g) * kTileN + et] = p.k_true * zg * p.zp_b - zg * colsum_v;
+          }
+        }
       }
       if (KIND == kKindI8) rc.row_corr = p.zp_b * (rs + rs1 + rs2);
       bool use_row = false;                              // takes part in the fused FindMinMax
@@ -555,14 +568,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         float v[32];
         float cmin = FLT_MAX, cmax = -FLT_MAX;           // this chunk's share of FindMinMax
         switch (flags) {
-          case 0: epi_math<KIND, false, false, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 1: epi_math<KIND, true, false, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 2: epi_math<KIND, false, true, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 3: epi_math<KIND, true, true, false>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 4: epi_math<KIND, false, false, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 5: epi_math<KIND, true, false, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          case 6: epi_math<KIND, false, true, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
-          default: epi_math<KIND, true, true, true>(raw, v, sp, pcol, rc, cmin, cmax); break;
+          case 0: epi_math<KIND, false, false, false>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 1: epi_math<KIND, true, false, false>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 2: epi_math<KIND, false, true, false>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 3: epi_math<KIND, true, true, false>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 4: epi_math<KIND, false, false, true>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 5: epi_math<KIND, true, false, true>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          case 6: epi_math<KIND, false, true, true>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
+          default: epi_math<KIND, true, true, true>(raw, v, sp, corr_off, pcol, rc, cmin, cmax); break;
         }
         if (col0 + 32 > p.N || p.out_acc) {              // rare: ragged N, or the debug dump
           cmin = FLT_MAX;
@@ -571,7 +584,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
             if (KIND == kKindI8 && p.out_acc && my_row < p.M && col < p.N) {
-              const int32_t cj = reinterpret_cast<const int32_t *>(sp)[3 * kTileN + pcol + j];
+              const int32_t cj = reinterpret_cast<const int32_t *>(sp)[corr_off + pcol + j];
               p.out_acc[(int64_t)my_row * p.ld_out + col] = (int32_t)raw[j] + (cj - rc.row_corr);
             }
             if (col >= p.N) {
@@ -764,7 +777,7 @@ int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t 
   return CE_GPU_OK;
 }
 
-template <int KIND, int CG>
+template <int KIND, int CG, bool GRAN = false>
 int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   using C = Cfg<CG>;
   CUtensorMap ma0, ma1, mb0, mb1, mo0, mo1;
@@ -788,7 +801,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   int dev = 0;
   CE_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !configured[dev]) {
-    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND, CG, GRAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes));
     configured[dev] = true;
   }
@@ -812,7 +825,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(kProfGemm, s);
-  CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG>, ma0, ma1, mb0, mb1, mo0, mo1, args));
+  CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG, GRAN>, ma0, ma1, mb0, mb1, mo0, mo1, args));
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
@@ -839,15 +852,17 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
     return CE_GPU_EINVAL;
   }
   static const int cta_group = getenv("CE_GPU_CTA_GROUP") ? atoi(getenv("CE_GPU_CTA_GROUP")) : 2;
+  // granule mode only changes the int8 epilogue (the float kinds carry no per-utterance parameters)
+  const bool gran = args.gran != 0 && kind == kKindI8 && args.tile_utt != nullptr;
   if (cta_group == 1) {
     switch (kind) {
-      case kKindI8: return LaunchKind<kKindI8, 1>(ops, args, s);
+      case kKindI8: return gran ? LaunchKind<kKindI8, 1, true>(ops, args, s) : LaunchKind<kKindI8, 1>(ops, args, s);
       case kKindBF16: return LaunchKind<kKindBF16, 1>(ops, args, s);
       case kKindTF32: return LaunchKind<kKindTF32, 1>(ops, args, s);
     }
   } else {
     switch (kind) {
-      case kKindI8: return LaunchKind<kKindI8, 2>(ops, args, s);
+      case kKindI8: return gran ? LaunchKind<kKindI8, 2, true>(ops, args, s) : LaunchKind<kKindI8, 2>(ops, args, s);
       case kKindBF16: return LaunchKind<kKindBF16, 2>(ops, args, s);
       case kKindTF32: return LaunchKind<kKindTF32, 2>(ops, args, s);
     }

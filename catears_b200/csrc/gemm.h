@@ -15,6 +15,7 @@ constexpr int kTileM = 128;          // rows per CTA tile = UMMA M (cta_group::1
 constexpr int kTileN = 256;          // columns per CTA tile = UMMA N
 constexpr int kTileKBytes = 128;     // one 128-byte swizzle atom of K per pipeline stage
 constexpr int kMaxTaps = 8;
+constexpr int kRowGran = 32;         // rows per entry of the row -> utterance table (one epilogue warp)
 
 inline int KindEltBytes(int kind) { return kind == kKindI8 ? 1 : kind == kKindBF16 ? 2 : 4; }
 inline int KindTileK(int kind) { return kTileKBytes / KindEltBytes(kind); }   // elements
@@ -26,7 +27,9 @@ struct QParam {
 };
 
 // Geometry of one utterance inside the activation row space.  Every utterance owns a block of
-// rows starting at a multiple of kTileM, so that a GEMM tile never spans two utterances.
+// rows starting at a multiple of kTileM, so that a GEMM tile never spans two utterances -- or, for
+// batches of short blocks (the micro-batches of live streams), at a multiple of kRowGran, the 32
+// accumulator rows one epilogue warp drains (GemmArgs::gran).
 struct UttRows {
   int32_t row_off;   // first row of the block
   int32_t rows;      // P = T + left_context + right_context
@@ -57,7 +60,9 @@ struct GemmArgs {
   float scale_b;
   int32_t k_true;                // un-padded K = n_taps * C
   const QParam *qa;              // [n_utts] activation quantisation of each utterance
-  const int32_t *tile_utt;       // [ceil(M / kTileM)] utterance of each row tile; nullptr = 0
+  const int32_t *tile_utt;       // [ceil(M / kRowGran)] utterance of each 32-row granule; nullptr = 0
+  int32_t gran;                  // 0: blocks start at multiples of kTileM (one utterance per tile);
+                                 // 1: at multiples of kRowGran (int8: per-warp parameters)
   const UttRows *utts;           // [n_utts]; nullptr = one block of M rows
 
   // outputs (any may be nullptr)

@@ -42,7 +42,7 @@ minmax_kernel(const float *__restrict__ x, int64_t ld, int C, int M,
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
-  const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+  const int utt = tile_utt ? tile_utt[row / kRowGran] : 0;
   int pos = row, P = M;
   if (utts) {
     pos = row - utts[utt].row_off;
@@ -95,7 +95,7 @@ quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_
   const int lane = threadIdx.x & 31;
   const int warps = gridDim.x * (blockDim.x >> 5);
   for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += warps) {
-  const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+  const int utt = tile_utt ? tile_utt[row / kRowGran] : 0;
   const QParam p = qp[utt];
   const float zp = (float)p.zero_point;
   const float *r = x + (int64_t)row * ld_in;
@@ -262,7 +262,7 @@ quantize_rows_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, i
     const int row = row_of(i);
     if (i + 1 < n_rows) load_row(row_of(i + 1), nxt);
     if (row < M) {
-      const int utt = tile_utt ? tile_utt[row / kTileM] : 0;
+      const int utt = tile_utt ? tile_utt[row / kRowGran] : 0;
       if (utt != utt_cached) {                                       // warp-uniform
         QParam p;
         if (minmax) {
@@ -362,7 +362,7 @@ finalize_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  const int utt = tile_utt[row / kTileM];
+  const int utt = tile_utt[row / kRowGran];
   const UttRows ur = utts[utt];
   const int pos = row - ur.row_off;
   if (pos < left || pos >= ur.rows - right) return;
@@ -426,7 +426,7 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
   // rows are walked from the end: the output-layer GEMM wrote those last (L2)
   for (int rr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < M; rr += warps) {
   const int row = M - 1 - rr;
-  const int utt = tile_utt[row / kTileM];
+  const int utt = tile_utt[row / kRowGran];
   const UttRows ur = utts[utt];
   const int pos = row - ur.row_off;
   if (pos < left || pos >= ur.rows - right) continue;
@@ -563,7 +563,7 @@ __device__ __forceinline__ int64_t OutputRowOf(int row, const int32_t *__restric
                                                const UttRows *__restrict__ utts,
                                                const int64_t *__restrict__ out_row_off, int left,
                                                int right) {
-  const int utt = tile_utt[row / kTileM];
+  const int utt = tile_utt[row / kRowGran];
   const UttRows ur = utts[utt];
   const int pos = row - ur.row_off;
   if (pos < left || pos >= ur.rows - right) return -1;

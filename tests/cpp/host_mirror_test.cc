@@ -262,10 +262,18 @@ static int StreamBench(char **argv) {
     if (!st.ok()) return Fail("cmvn stats", st);
   }
   const double host_ms = TimeCalls(StreamBatch(&am, stats, 0), n, per_call, calls);
+  ce_gpu_profile_enable(1);                                // kernel time of the device-state calls
+  double kernel_ms[CE_GPU_PROFILE_CATEGORIES];
+  int64_t launches[CE_GPU_PROFILE_CATEGORIES];
   const double dev_ms = TimeCalls(DeviceStreamBatch(&am, n), n, per_call, calls);
+  ce_gpu_profile_read(kernel_ms, launches);
+  ce_gpu_profile_enable(0);
   if (host_ms < 0 || dev_ms < 0) return Fail("Process", Status::RuntimeError("streambench"));
-  printf("streams=%d samples_per_call=%d row_words=%d host_state_ms=%.3f device_state_ms=%.3f\n", n, per_call,
-         am.output_width(), host_ms, dev_ms);
+  double gpu_ms = 0.0;
+  for (double v : kernel_ms) gpu_ms += v;
+  printf("streams=%d samples_per_call=%d row_words=%d host_state_ms=%.3f device_state_ms=%.3f "
+         "(kernels %.3f ms per call: gemm %.3f)\n", n, per_call, am.output_width(), host_ms, dev_ms,
+         gpu_ms / (calls + 3), kernel_ms[2] / (calls + 3));
   return 0;
 }
 

@@ -62,10 +62,15 @@ def test_am_u8_reference_vectors_bit_exact(golden, models):
     assert check_argmax(am, r["am_u8"]) > 0.98
 
 
-def test_am_u8_ragged_batch_bit_exact_vs_oracle(port, models, small_model):
+@pytest.mark.parametrize("layout", ["auto", "32", "128"])
+def test_am_u8_ragged_batch_bit_exact_vs_oracle(port, models, small_model, monkeypatch, layout):
     """Batch of utterances of T = 1, 2, 7, 57, 130, 300 (T=1..7 exercise the rows-actually-read
     rule of the fused FindMinMax); accumulators of the last layer and log-likelihoods per
-    utterance against the oracle run one utterance at a time."""
+    utterance against the oracle run one utterance at a time.  The row space packs these short
+    blocks at multiples of 32 rows (granule-mode int8 epilogue: another utterance in every quadrant
+    of a GEMM tile); both layouts are also forced."""
+    if layout != "auto":
+        monkeypatch.setenv("CE_GPU_ROW_GRAN", layout)
     rng = np.random.default_rng(21)
     sizes = [1, 57, 2, 130, 7, 300]
     feats = rng.standard_normal((sum(sizes), 40)).astype(np.float32) * 2.0
@@ -98,11 +103,12 @@ def test_am_float_ragged_batch_vs_oracle(port, models, small_model):
         assert np.abs(ll[off[u]:off[u + 1]] - want).max() < 1e-3, T
 
 
-def test_batch_equals_singles_and_chunking(models):
-    """Property: batch-of-N == N singles, bit for bit (int8), for any chunking of the batch."""
-    import os
+@pytest.mark.parametrize("layout", ["32", "128"])
+def test_batch_equals_singles_and_chunking(models, monkeypatch, layout):
+    """Property: batch-of-N == N singles, bit for bit (int8), in both row-space layouts."""
+    monkeypatch.setenv("CE_GPU_ROW_GRAN", layout)
     rng = np.random.default_rng(23)
-    sizes = [90, 150, 40, 260]
+    sizes = [90, 150, 40, 260, 5, 31, 33]
     feats = rng.standard_normal((sum(sizes), 40)).astype(np.float32)
     off = np.concatenate([[0], np.cumsum(sizes)])
     m = models["int8"]
