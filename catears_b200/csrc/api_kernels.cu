@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) segcopy_kernel(const SegCopy *__restrict_
 
 int SegCopyLaunch(const SegCopy *segs_dev, int n, cudaStream_t s) {
   if (n <= 0) return CE_GPU_OK;
+  ProfScope prof(kProfOther, s);
   segcopy_kernel<<<n, 256, 0, s>>>(segs_dev);
   CE_LAUNCHED();
   return CE_GPU_OK;

@@ -271,9 +271,11 @@ static int StreamBench(char **argv) {
   if (host_ms < 0 || dev_ms < 0) return Fail("Process", Status::RuntimeError("streambench"));
   double gpu_ms = 0.0;
   for (double v : kernel_ms) gpu_ms += v;
+  const double per = 1.0 / (calls + 3);
   printf("streams=%d samples_per_call=%d row_words=%d host_state_ms=%.3f device_state_ms=%.3f "
-         "(kernels %.3f ms per call: gemm %.3f)\n", n, per_call, am.output_width(), host_ms, dev_ms,
-         gpu_ms / (calls + 3), kernel_ms[2] / (calls + 3));
+         "(kernels %.3f ms per call: fbank %.3f cmvn %.3f gemm %.3f quantize %.3f finalize %.3f copies %.3f)\n",
+         n, per_call, am.output_width(), host_ms, dev_ms, gpu_ms * per, kernel_ms[0] * per, kernel_ms[1] * per,
+         kernel_ms[2] * per, kernel_ms[3] * per, kernel_ms[4] * per, kernel_ms[5] * per);
   return 0;
 }
 
