@@ -10,6 +10,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -216,8 +217,8 @@ static int Streams(int argc, char **argv) {
 
 // streambench <conf> <precision> <cmvn_stats.vec0 | -> <n_streams> <samples_per_call> <calls>
 // Serving-shaped timing: n live streams each receive samples_per_call new samples per call; wall
-// milliseconds per call for host-resident (StreamBatch) and device-resident (DeviceStreamBatch)
-// state.  Not a test: tools/stream_probe.py runs it.
+// milliseconds per call (median) for host-resident (StreamBatch) and device-resident
+// (DeviceStreamBatch) state.  Not a test: tools/stream_probe.py runs it.
 template <typename Batch>
 static double TimeCalls(const Batch &batch, int n, int per_call, int calls) {
   std::vector<typename Batch::Stream> state(n);
@@ -236,16 +237,17 @@ static double TimeCalls(const Batch &batch, int n, int per_call, int calls) {
   const std::vector<int> cnt(n, per_call);
   const std::vector<bool> eos(n, false);
   std::vector<Matrix> out;
-  double ms = 0.0;
+  std::vector<double> ms;
   for (int c = 0; c < calls + 3; ++c) {                     // 3 warm-up calls
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     Status st = batch.Process(streams, pcm, cnt, eos, &out);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (!st.ok()) return -1.0;
-    if (c >= 3) ms += 1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec);
+    if (c >= 3) ms.push_back(1e3 * (t1.tv_sec - t0.tv_sec) + 1e-6 * (t1.tv_nsec - t0.tv_nsec));
   }
-  return ms / calls;
+  std::sort(ms.begin(), ms.end());                          // the median: the shared boxes hiccup
+  return ms[ms.size() / 2];
 }
 
 static int StreamBench(char **argv) {

@@ -23,7 +23,7 @@ def main():
     env = dict(os.environ, HOST_MIRROR_SELECT=os.environ.get("HOST_MIRROR_SELECT", "topk:64"))
     for n, ms in ((64, 100), (512, 100), (512, 500), (2048, 100)):
         subprocess.check_call([exe, "streambench", os.path.join(d, "tdnn.conf"), "0", os.path.join(d, "tdnn.cmvn"),
-                               str(n), str(16 * ms), "10"], stdin=subprocess.DEVNULL, timeout=240, env=env)
+                               str(n), str(16 * ms), "21"], stdin=subprocess.DEVNULL, timeout=240, env=env)
 
 
 if __name__ == "__main__":
