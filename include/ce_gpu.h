@@ -15,6 +15,12 @@
  *   ce_gpu_quantize   Quantize              src/matrix.cc:366-387
  *   ce_gpu_gemm_u8    MatMat_U8U8F32        src/matrix.cc:389-420
  *   ce_gpu_last_error ce_stt_last_error     src/ce_stt.cc:375-377 (thread-local here)
+ *   ce_gpu_streams_*  the per-utterance state of Fbank::Instance (src/fbank.cc:275-313), CMVN
+ *                     (src/cmvn.cc:35-68) and AcousticModel::Instance (src/am.cc:115-142), kept in
+ *                     device buffers for many live utterances at once
+ *   ce_gpu_model_set_output / ce_gpu_model_set_rows_callback
+ *                     what Decoder::Process reads of a row (src/decoder.cc:97-102) and when it
+ *                     may start reading (src/ce_stt.cc:349-357): narrower rows, per-chunk hand-over
  *
  * Conventions
  *   - Plain pointers and sizes only.  Every DATA pointer (pcm, feats, loglik, argmax, A, B, C...)
