@@ -193,11 +193,20 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
   CE_CHECK(UseDevice(m->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  // Every batched copy of the call is planned first (they are executed in four groups, in stream
-  // order around the three compute passes).
+  // Every batched copy of the call is planned first (they are executed in six groups, in stream
+  // order around the three compute passes).  One CTA copies one entry, so long copies (a minute of
+  // rows, a full CMVN history) are cut into 256 KB pieces.
   std::vector<SegCopy> seg;
   auto add = [&seg](const void *src, void *dst, size_t bytes, uint32_t repeat = 1) {
-    if (bytes > 0 && repeat > 0) seg.push_back(SegCopy{src, dst, (uint32_t)bytes, repeat});
+    if (bytes == 0 || repeat == 0) return;
+    constexpr size_t kPiece = 256 * 1024;
+    if (repeat > 1 || bytes <= kPiece) {
+      seg.push_back(SegCopy{src, dst, (uint32_t)bytes, repeat});
+      return;
+    }
+    for (size_t o = 0; o < bytes; o += kPiece)
+      seg.push_back(SegCopy{static_cast<const char *>(src) + o, static_cast<char *>(dst) + o,
+                            (uint32_t)std::min(kPiece, bytes - o), 1});
   };
   CE_CHECK(S->pcm_new.Reserve(sizeof(int16_t) * (size_t)std::max<int64_t>(new_total, 1)));
   CE_CHECK(S->wave.Reserve(sizeof(int16_t) * (size_t)std::max<int64_t>(wave_total, 1)));

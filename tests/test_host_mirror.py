@@ -224,6 +224,12 @@ def test_stream_set_slot_reuse_and_row_capacity(tmp_path, golden):
             assert np.abs(rows - whole).max() < 1e-5
         with pytest.raises(api.CeGpuError):
             s.process([sb], [None], [False])                 # ended: not open any more
+        big = synth.synth_utterance(75, 192000)              # 12 s in ONE call: 460 KB of rows, copied in pieces
+        sd = s.open()
+        rows_big = s.process([sd], [big], [True])[0]
+        whole, _, _ = am.forward(big)
+        assert rows_big.shape == whole.shape == (1198, 96)
+        assert np.abs(rows_big - whole).max() < 1e-5
     finally:
         s.close()
         am.close()
