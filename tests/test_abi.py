@@ -81,3 +81,23 @@ def test_model_load_errors(tmp_path, small_model):
     if not torch.cuda.is_available():
         with pytest.raises(api.CeGpuError, match="no CUDA device"):
             api.AcousticModelGpu(config=small_model["conf"])
+
+
+def test_null_handles_are_rejected_not_dereferenced():
+    """Every handle-taking entry point of the decoder-feed and streaming additions answers a NULL
+    handle with an error code and a message (the reference asserts; here it is CE_GPU_EINVAL)."""
+    L = api.lib()
+    ids = (C.c_int32 * 2)(0, 1)
+    assert L.ce_gpu_model_set_output(None, 1, ids, 2) < 0
+    assert "null model" in api.last_error()
+    assert L.ce_gpu_model_output_width(None) < 0
+    assert L.ce_gpu_model_set_rows_callback(None, api.ROWS_READY_FN(0), None) < 0
+    assert not L.ce_gpu_streams_create(None, 4)
+    assert "bad arguments" in api.last_error()
+    assert L.ce_gpu_streams_open(None) < 0
+    slots = (C.c_int * 1)(0)
+    cnt = (C.c_int * 1)(160)
+    assert L.ce_gpu_streams_rows_ready(None, slots, 1, cnt, None) < 0
+    off = (C.c_int64 * 2)()
+    assert L.ce_gpu_streams_process(None, slots, 1, None, cnt, None, None, 0, off, None) < 0
+    L.ce_gpu_streams_free(None)                              # like free(NULL)
