@@ -11,6 +11,11 @@
 //   ce_host::AcousticModel::EndOfStream                        src/am.h:47,     src/am.cc:144-164
 //   TransitionPdfIdMap(), num_pdfs()                           src/am.h:37-39,50
 //
+// Beyond the reference's surface (serving forms of the same operators):
+//   ce_host::AcousticModel::SelectPdfs / SelectTopK   narrower log_prob rows for the decoder
+//   ce_host::StreamBatch         many live utterances per call, per-stream state on the host
+//   ce_host::DeviceStreamBatch   the same with the state in device buffers (ce_gpu_streams_*)
+//
 // Differences, all deliberate: the types are plain (std::vector-backed Matrix instead of
 // pocketkaldi::Matrix<float>); every call that can fail on the device returns a Status instead of
 // asserting; there is no CPU implementation behind any of it (no device -> Status with the
