@@ -604,6 +604,53 @@ def run_longform(args):
         dist.destroy_process_group()
 
 
+def run_streaming(args):
+    """The streaming form: --streams live utterances, each receiving
+    --stream-ms milliseconds of new audio per micro-batch call through ce_gpu_streams_* (per-stream
+    state on the device), rows = the 64 best (loglik, pdf) pairs per frame to the host.  One step =
+    one call; wall time per call (the call returns with the rows on the host) and the kernel time
+    inside it.  Single GPU."""
+    import time
+    from catears_b200 import api, synth
+    conf = os.path.join(model_dir(), "tdnn.conf")
+    model = api.AcousticModelGpu(config=conf, precision=args.precision)
+    model.set_output("topk", k=64)
+    n, per_call = args.streams, 16 * args.stream_ms
+    streams = api.StreamSet(model, n)
+    slots = [streams.open() for _ in range(n)]
+    audio = synth.synth_utterance(11, per_call * (args.steps + args.warmup + 1), seed=11)
+    eos = [False] * n
+
+    def step(c):
+        piece = audio[c * per_call:(c + 1) * per_call]
+        return streams.process(slots, [piece] * n, eos)
+    for c in range(args.warmup):
+        step(c)
+    api.profile_enable(True)
+    wall = []
+    for c in range(args.warmup, args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rows = step(c)
+        wall.append(1e3 * (time.perf_counter() - t0))
+    prof = api.profile_read()
+    api.profile_enable(False)
+    ms = float(np.median(wall))
+    print(json.dumps({
+        "metric": METRIC, "value": round(n * args.stream_ms * 1e-3 / (ms * 1e-3), 1), "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
+        "data": "synthetic",
+        "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+        "config": {"workload": "streaming: %d live streams x %d ms of new audio per call "
+                               "(ce_gpu_streams_process, state on the device), fbank + CMVN + TDNN, %s GEMMs, "
+                               "rows = 64 best (loglik, pdf) pairs per frame to the host; median wall time per call"
+                               % (n, args.stream_ms, args.precision),
+                   "rows_per_step": int(sum(r.shape[0] for r in rows))}}))
+    streams.close()
+    model.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -616,9 +663,12 @@ def main():
     ap.add_argument("--e2e-loglik", action="store_true")
     ap.add_argument("--e2e-topk", type=int, default=0,
                     help="also time e2e with the k best (loglik, pdf) pairs per frame copied to the host")
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "frontend", "longform"],
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "frontend", "longform", "streaming"],
                     help="pipeline = the headline fbank+CMVN+AM step (default); frontend = config 2; "
-                         "longform = config 5 (one hour in time shards)")
+                         "longform = config 5 (one hour in time shards); streaming = live streams in "
+                         "micro-batches (one GPU)")
+    ap.add_argument("--streams", type=int, default=512)
+    ap.add_argument("--stream-ms", type=int, default=100)
     ap.add_argument("--frontend-utts", type=int, default=10000)
     ap.add_argument("--mel", type=int, default=40)
     args = ap.parse_args()
@@ -626,6 +676,8 @@ def main():
         args.warmup = max(args.warmup, 1)
     if args.workload == "frontend" and args.impl == "native":
         run_frontend(args)
+    elif args.workload == "streaming" and args.impl == "native":
+        run_streaming(args)
     elif args.workload == "longform" and args.impl == "native":
         if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
             os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
