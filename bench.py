@@ -32,6 +32,7 @@ UNIT = "audio-s/s"
 UTT_SECONDS = 10.0
 FLOPS_PER_FRAME = 38158336          # 2*(200*1024 + 5*3072*1024 + 1024*3072)
 FBANK_BYTES_PER_FRAME = 480         # 160 samples * 2 B + 40 mel * 4 B
+DTYPES = {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32", "bf16x3": "bf16x3"}
 
 
 def workload_config(utts_per_gpu, world, precision):
@@ -382,6 +383,9 @@ def run_gpu(args):
     elif args.precision == "bf16":
         tensor_peak = bf16_sustained
         peak_note = "bf16_tflops_sustained; %s" % peak_src
+    elif args.precision == "bf16x3":
+        tensor_peak = bf16_sustained / 3.0
+        peak_note = "bf16_tflops_sustained / 3 (three bf16 products per algorithmic multiply-add); %s" % peak_src
     else:
         tensor_peak = 0.5 * bf16_sustained
         peak_note = "0.5 x bf16_tflops_sustained (tf32 rate is half the bf16 rate%s); %s" % (
@@ -419,7 +423,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
+        "dtype": DTYPES[args.precision],
         "data": "synthetic",
         "config": workload_config(n_utts, world, args.precision),
         "clocks": clocks,
@@ -592,7 +596,7 @@ def run_longform(args):
             "metric": METRIC, "value": round(3600.0 * args.steps / (ms * 1e-3), 1), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
+            "dtype": DTYPES[args.precision],
             "data": "synthetic",
             "config": {"workload": "config 5: one hour of 16 kHz audio (%d frames) in %d time shards with "
                                    "recomputed halos (L + 600 CMVN-history frames before, R after), %d shard(s) "
@@ -639,7 +643,7 @@ def run_streaming(args):
         "metric": METRIC, "value": round(n * args.stream_ms * 1e-3 / (ms * 1e-3), 1), "unit": UNIT,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"int8": "u8", "bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision],
+        "dtype": DTYPES[args.precision],
         "data": "synthetic",
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
         "config": {"workload": "streaming: %d live streams x %d ms of new audio per call "
@@ -657,7 +661,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="int8", choices=["int8", "bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="int8", choices=["int8", "bf16", "tf32", "fp32", "bf16x3"])
     ap.add_argument("--utts-per-gpu", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-loglik", action="store_true")

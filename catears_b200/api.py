@@ -14,8 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libce_gpu.so")
 
-PRECISION_INT8, PRECISION_BF16, PRECISION_FP32, PRECISION_TF32 = 0, 1, 2, 3
-PRECISIONS = {"int8": 0, "bf16": 1, "fp32": 2, "tf32": 3}
+PRECISION_INT8, PRECISION_BF16, PRECISION_FP32, PRECISION_TF32, PRECISION_BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"int8": 0, "bf16": 1, "fp32": 2, "tf32": 3, "bf16x3": 4}
 
 FRAME_LEN, FRAME_SHIFT = 400, 160
 
@@ -29,6 +29,7 @@ EXPORTS = [
     "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
     "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback", "ce_gpu_streams_create",
     "ce_gpu_streams_free", "ce_gpu_streams_open", "ce_gpu_streams_rows_ready", "ce_gpu_streams_process",
+    "ce_gpu_nnet_get_qparams",
 ]
 ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
@@ -84,6 +85,7 @@ def lib():
     L.ce_gpu_streams_process.argtypes = [vp, ip, C.c_int, C.POINTER(vp), ip, C.POINTER(C.c_ubyte), vp,
                                          C.c_int64, i64p, vp]
     L.ce_gpu_nnet_get_acc.argtypes = [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ce_gpu_nnet_get_qparams.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
     L.ce_gpu_quantize.argtypes = [vp, C.c_int64, C.c_int, vp, C.POINTER(C.c_float),
                                   C.POINTER(C.c_int32), C.c_int, vp]
     L.ce_gpu_gemm_u8.argtypes = [vp, C.c_float, C.c_int32, vp, C.c_float, C.c_int32, C.c_int, C.c_int,
@@ -387,6 +389,14 @@ class AcousticModelGpu:
         _check(lib().ce_gpu_nnet_get_acc(self._h, utt, acc.ctypes.data, acc.size, C.byref(r), C.byref(c)),
                "ce_gpu_nnet_get_acc")
         return acc
+
+
+    def get_qparams(self, utt=0):
+        """(scale[], zero_point[]) of the activation Quantize in front of every Linear layer."""
+        sc = (C.c_float * 64)()
+        zp = (C.c_int32 * 64)()
+        n = _check(lib().ce_gpu_nnet_get_qparams(self._h, utt, sc, zp, 64), "ce_gpu_nnet_get_qparams")
+        return np.array(sc[:n], np.float32), np.array(zp[:n], np.int32)
 
 
 class StreamSet:

@@ -484,6 +484,30 @@ int ce_gpu_nnet_get_acc(ce_gpu_model_t *m, int utt, int32_t *acc, int64_t cap, i
   return CE_GPU_OK;
 }
 
+// The activation QuantizationParams (src/matrix.h:231-234) every Linear layer's Quantize produced
+// for utterance `utt` of the last (one-chunk) forward call on an int8 model.
+int ce_gpu_nnet_get_qparams(ce_gpu_model_t *m, int utt, float *scale, int32_t *zero_point, int cap) {
+  if (!m || m->kind != ce::kKindI8 || utt < 0 || utt >= m->last_n_utts) {
+    SetError("ce_gpu_nnet_get_qparams: needs an int8 model and an utterance of the last forward call");
+    return CE_GPU_EINVAL;
+  }
+  const int nb = (int)m->blocks.size();
+  if (cap < nb) {
+    SetError("ce_gpu_nnet_get_qparams: %d layers, room for %d", nb, cap);
+    return CE_GPU_EINVAL;
+  }
+  CE_CHECK(UseDevice(m->device));
+  CE_CUDA(cudaDeviceSynchronize());
+  for (int b = 0; b < nb; ++b) {
+    ce::QParam q;
+    CE_CUDA(cudaMemcpy(&q, m->ws[0].qparams.as<ce::QParam>() + (size_t)b * m->last_n_utts + utt, sizeof(q),
+                       cudaMemcpyDeviceToHost));
+    if (scale) scale[b] = q.scale;
+    if (zero_point) zero_point[b] = q.zero_point;
+  }
+  return nb;
+}
+
 // ---- multi-GPU planning ---------------------------------------------------------------------
 
 int ce_gpu_partition(const int64_t *utt_frame_offsets, int n_utts, int n_parts, int32_t *part_begin) {
@@ -647,8 +671,9 @@ int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *
     case CE_GPU_PRECISION_BF16: kind = kKindBF16; break;
     case CE_GPU_PRECISION_FP32: kind = kKindTF32; n_pass = 3; break;
     case CE_GPU_PRECISION_TF32: kind = kKindTF32; break;
+    case CE_GPU_PRECISION_BF16X3: kind = kKindBF16X3; break;
     default:
-      SetError("ce_gpu_gemm_f32: precision must be BF16, FP32 or TF32");
+      SetError("ce_gpu_gemm_f32: precision must be BF16, FP32, TF32 or BF16X3");
       return CE_GPU_EINVAL;
   }
   CE_CHECK(UseDevice(device));
@@ -659,7 +684,7 @@ int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *
   CE_CHECK(StageIn(b, sizeof(float) * (size_t)k * n, &ws->in2, s, &b_dev));
   const int k_pad = RoundUp(k, KindTileK(kind));
   const int ldc = RoundUp(n, 4);
-  const size_t elt = KindEltBytes(kind);
+  const size_t elt = (size_t)KindEltBytes(kind) * (kind == kKindBF16X3 ? 2 : 1);   // stored bytes per channel
   CE_CHECK(ws->tmp[0].Reserve(sizeof(float) * (size_t)n * k));        // B^T fp32
   CE_CHECK(ws->tmp[1].Reserve(elt * (size_t)m * k_pad));              // A operand (hi)
   CE_CHECK(ws->tmp[2].Reserve(elt * (size_t)m * k_pad));              // A lo
@@ -667,7 +692,12 @@ int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *
   CE_CHECK(ws->tmp[4].Reserve(elt * (size_t)n * k_pad));              // B lo
   CE_CHECK(ws->tmp[5].Reserve(sizeof(float) * (size_t)m * ldc));
   CE_CHECK(TransposePadLaunch<float>(static_cast<const float *>(b_dev), k, n, ws->tmp[0].as<float>(), k, s));
-  if (kind == kKindBF16) {
+  if (kind == kKindBF16X3) {
+    CE_CHECK(ConvertLaunch(static_cast<const float *>(a_dev), k, k, m, k_pad, nullptr, nullptr, nullptr, s,
+                           ws->tmp[1].as<__nv_bfloat16>()));
+    CE_CHECK(ConvertLaunch(ws->tmp[0].as<float>(), k, k, n, k_pad, nullptr, nullptr, nullptr, s,
+                           ws->tmp[3].as<__nv_bfloat16>()));
+  } else if (kind == kKindBF16) {
     CE_CHECK(ConvertLaunch(static_cast<const float *>(a_dev), k, k, m, k_pad,
                            ws->tmp[1].as<__nv_bfloat16>(), nullptr, nullptr, s));
     CE_CHECK(ConvertLaunch(ws->tmp[0].as<float>(), k, k, n, k_pad, ws->tmp[3].as<__nv_bfloat16>(),
@@ -680,7 +710,7 @@ int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *
   }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  g.M = m; g.N = n; g.c_pad = k_pad; g.n_taps = 1; g.n_pass = n_pass;
+  g.M = m; g.N = n; g.c_pad = KindPhysCols(kind, k_pad); g.n_taps = 1; g.n_pass = n_pass;
   if (n_pass == 3) {
     g.pass_a[0] = 1; g.pass_b[0] = 0;
     g.pass_a[1] = 0; g.pass_b[1] = 1;
@@ -692,7 +722,7 @@ int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *
   memset(&ops, 0, sizeof(ops));
   ops.a[0] = ws->tmp[1].ptr; ops.a[1] = n_pass == 3 ? ws->tmp[2].ptr : nullptr; ops.rows_a = m;
   ops.b[0] = ws->tmp[3].ptr; ops.b[1] = n_pass == 3 ? ws->tmp[4].ptr : nullptr; ops.rows_b = n;
-  ops.k_total = k_pad;
+  ops.k_total = KindPhysCols(kind, k_pad);
   CE_CHECK(GemmLaunch(kind, ops, g, s));
   CE_CUDA(cudaMemcpy2DAsync(c, sizeof(float) * n, ws->tmp[5].ptr, sizeof(float) * ldc, sizeof(float) * n, m,
                             IsDevicePtr(c) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));

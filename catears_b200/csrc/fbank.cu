@@ -587,10 +587,13 @@ int FbankLaunch(const int16_t *pcm_dev, int64_t total_samples, const int64_t *sa
   CE_CHECK(chunks->Upload(bytes, s));
 
   SmemLayout L = MakeLayout(dt.n_weights);
-  static thread_local int configured_smem = 0;
-  if (L.total > configured_smem) {
+  // the opt-in above the 48 KB default is a per-DEVICE attribute: one host thread may drive several
+  static thread_local int configured_smem[64] = {0};
+  int dev = 0;
+  CE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || L.total > configured_smem[dev]) {
     CE_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    configured_smem = L.total;
+    if (dev < 64) configured_smem[dev] = L.total;
   }
   ProfScope prof(kProfFbank, s);
   fbank_kernel<<<(unsigned)n_chunks, kThreads, L.total, s>>>(

@@ -192,11 +192,11 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
                                        uint32_t idesc, uint32_t accumulate) {
   if (CG == 1) {
     if (KIND == kKindI8) CE_TC_MMA("1", "i8");
-    else if (KIND == kKindBF16) CE_TC_MMA("1", "f16");
+    else if (KIND == kKindBF16 || KIND == kKindBF16X3) CE_TC_MMA("1", "f16");
     else CE_TC_MMA("1", "tf32");
   } else {
     if (KIND == kKindI8) CE_TC_MMA("2", "i8");
-    else if (KIND == kKindBF16) CE_TC_MMA("2", "f16");
+    else if (KIND == kKindBF16 || KIND == kKindBF16X3) CE_TC_MMA("2", "f16");
     else CE_TC_MMA("2", "tf32");
   }
 }
@@ -232,7 +232,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 template <int KIND, int CG>
 __device__ __forceinline__ uint32_t make_idesc() {
   const uint32_t c_fmt = (KIND == kKindI8) ? 2u : 1u;                 // S32 : F32
-  const uint32_t ab_fmt = (KIND == kKindI8) ? 0u : (KIND == kKindBF16) ? 1u : 2u;   // U8, BF16, TF32
+  const uint32_t ab_fmt = (KIND == kKindI8) ? 0u : (KIND == kKindTF32) ? 2u : 1u;   // U8, TF32, BF16
   return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
          ((uint32_t)((kTileM * CG) >> 4) << 24);                      // M = 128 (one CTA) / 256 (pair)
 }
@@ -374,7 +374,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int m_tiles = (p.M + kGroupM - 1) / kGroupM;
   const int n_tiles = (p.N + kTileN - 1) / kTileN;
   const int total_tiles = m_tiles * n_tiles;
-  constexpr int kEltBytes = (KIND == kKindI8) ? 1 : (KIND == kKindBF16) ? 2 : 4;
+  constexpr int kEltBytes = (KIND == kKindI8) ? 1 : (KIND == kKindTF32) ? 4 : 2;
   constexpr int kTileK = kTileKBytes / kEltBytes;
   const int kb_per_tap = p.c_pad / kTileK;
   const int steps_per_pass = p.n_taps * kb_per_tap;
@@ -435,7 +435,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           tc_fence_after();
           const uint64_t da = make_desc(smem_u32(smem_a + stage * kABytes));
           const uint64_t db = make_desc(smem_u32(smem_b + stage * kBBytes));
-          if (!(p.debug & 2)) {
+          if (KIND == kKindBF16X3) {
+            // atom = [32 hi | 32 lo]: K steps 0,1 are hi, 2,3 lo.  Small terms first: lo*hi, hi*lo, hi*hi.
+            constexpr int ka[6] = {2, 3, 0, 1, 0, 1};
+            constexpr int kb[6] = {0, 1, 2, 3, 0, 1};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              tc_mma<KIND, CG>(tmem_d, da + (uint64_t)(2 * ka[i]), db + (uint64_t)(2 * kb[i]), idesc,
+                               (step | i) != 0 ? 1u : 0u);
+            }
+          } else if (!(p.debug & 2)) {
 #pragma unroll
             for (int k = 0; k < kTileKBytes / 32; ++k) {
               // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
@@ -600,7 +609,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
 
         // ---- registers -> swizzled staging tile -> one TMA store per 32 x 128 B ----
         const int sw = lane & 7;
-        if (KIND == kKindBF16 && p.out_bf16) {
+        if (KIND == kKindBF16X3 && p.out_bf16) {
+          // the next layer's operand: 32 columns -> one 128-byte atom [32 hi | 32 lo] per row
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = v[8 * q + 2 * e], x1 = v[8 * q + 2 * e + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+              wh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              wl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4 *>(stg + lane * 128 + ((q ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4 *>(stg + lane * 128 + (((4 + q) ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&map_o0, stg_u32, 2 * col0, m0 + quad * 32);
+        } else if (KIND == kKindBF16 && p.out_bf16) {
           if ((c & 1) == 0) {                            // a new 64-column tile: previous store must
             if (lane == 0) tma_store_wait_read();        // have finished reading the buffer
             __syncwarp();
@@ -728,8 +759,8 @@ int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows
   CE_CHECK(GetEncodeFn(&fn));
   const int elt = KindEltBytes(kind);
   const CUtensorMapDataType dt = kind == kKindI8     ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                                 : kind == kKindBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+                                 : kind == kKindTF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * elt) % 16 != 0) {
     SetError("GEMM operand is not 16-byte aligned (base %p, row pitch %lld bytes)", base,
              (long long)(cols * elt));
@@ -781,13 +812,14 @@ template <int KIND, int CG, bool GRAN = false>
 int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   using C = Cfg<CG>;
   CUtensorMap ma0, ma1, mb0, mb1, mo0, mo1;
-  const bool out_is_bf16 = (KIND == kKindBF16) && args.out_bf16 != nullptr;
+  const bool out_is_bf16 = (KIND == kKindBF16 || KIND == kKindBF16X3) && args.out_bf16 != nullptr;
   const void *o0 = out_is_bf16 ? static_cast<const void *>(args.out_bf16) : static_cast<const void *>(args.out_f32);
   if (o0 == nullptr) {
     SetError("GemmLaunch: no output buffer");
     return CE_GPU_EINVAL;
   }
-  CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M, args.n_store, args.ld_out, &mo0));
+  CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M,
+                      (KIND == kKindBF16X3 && out_is_bf16) ? 2 * args.n_store : args.n_store, args.ld_out, &mo0));
   if (args.out_lo) {
     CE_CHECK(MakeOutMap(false, args.out_lo, args.M, args.n_store, args.ld_out, &mo1));
   } else {
@@ -836,13 +868,15 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
   GemmArgs args = args_in;
   static const int debug_bits = getenv("CE_GPU_GEMM_DEBUG") ? atoi(getenv("CE_GPU_GEMM_DEBUG")) : 0;
   args.debug = debug_bits;
-  if (args.c_pad <= 0 || args.c_pad % KindTileK(kind) != 0 || args.n_taps < 1 ||
+  if (args.c_pad <= 0 || (args.c_pad * KindEltBytes(kind)) % kTileKBytes != 0 || args.n_taps < 1 ||
       args.n_taps > kMaxTaps || args.n_pass < 1 || args.n_pass > 3) {
     SetError("GemmLaunch: bad geometry (c_pad %d, taps %d, passes %d)", args.c_pad, args.n_taps,
              args.n_pass);
     return CE_GPU_EINVAL;
   }
-  if (args.n_store < args.N || args.n_store > args.ld_out) {
+  const bool x3_operand_out = kind == kKindBF16X3 && args.out_bf16 != nullptr;
+  if (args.n_store < args.N || (x3_operand_out ? 2 * args.n_store : args.n_store) > args.ld_out ||
+      (x3_operand_out && args.n_store % 32 != 0)) {
     SetError("GemmLaunch: n_store %d outside [N %d, ld_out %lld]", args.n_store, args.N,
              (long long)args.ld_out);
     return CE_GPU_EINVAL;
@@ -859,12 +893,14 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
       case kKindI8: return gran ? LaunchKind<kKindI8, 1, true>(ops, args, s) : LaunchKind<kKindI8, 1>(ops, args, s);
       case kKindBF16: return LaunchKind<kKindBF16, 1>(ops, args, s);
       case kKindTF32: return LaunchKind<kKindTF32, 1>(ops, args, s);
+      case kKindBF16X3: return LaunchKind<kKindBF16X3, 1>(ops, args, s);
     }
   } else {
     switch (kind) {
       case kKindI8: return gran ? LaunchKind<kKindI8, 2, true>(ops, args, s) : LaunchKind<kKindI8, 2>(ops, args, s);
       case kKindBF16: return LaunchKind<kKindBF16, 2>(ops, args, s);
       case kKindTF32: return LaunchKind<kKindTF32, 2>(ops, args, s);
+      case kKindBF16X3: return LaunchKind<kKindBF16X3, 2>(ops, args, s);
     }
   }
   SetError("GemmLaunch: unknown kind %d", kind);

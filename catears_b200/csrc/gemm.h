@@ -9,7 +9,11 @@
 
 namespace ce {
 
-enum GemmKind { kKindI8 = 0, kKindBF16 = 1, kKindTF32 = 2 };
+// kKindBF16X3: bf16 hi/lo split operands, three products per K element (hi*hi + hi*lo + lo*hi):
+// a 16-bit mantissa at the bf16 tensor rate.  Both operands are stored INTERLEAVED per 128-byte
+// K atom -- [32 hi | 32 lo] bf16 for 32 consecutive channels -- so one staged atom feeds all three
+// products (six K=16 MMAs) and the operand traffic is 2x, not 3x, that of plain bf16.
+enum GemmKind { kKindI8 = 0, kKindBF16 = 1, kKindTF32 = 2, kKindBF16X3 = 3 };
 
 constexpr int kTileM = 128;          // rows per CTA tile = UMMA M (cta_group::1)
 constexpr int kTileN = 256;          // columns per CTA tile = UMMA N
@@ -17,8 +21,11 @@ constexpr int kTileKBytes = 128;     // one 128-byte swizzle atom of K per pipel
 constexpr int kMaxTaps = 8;
 constexpr int kRowGran = 32;         // rows per entry of the row -> utterance table (one epilogue warp)
 
-inline int KindEltBytes(int kind) { return kind == kKindI8 ? 1 : kind == kKindBF16 ? 2 : 4; }
-inline int KindTileK(int kind) { return kTileKBytes / KindEltBytes(kind); }   // elements
+inline int KindEltBytes(int kind) { return kind == kKindI8 ? 1 : (kind == kKindBF16 || kind == kKindBF16X3) ? 2 : 4; }
+// logical K elements (channels) per 128-byte atom
+inline int KindTileK(int kind) { return kind == kKindBF16X3 ? 32 : kTileKBytes / KindEltBytes(kind); }
+// stored elements per row for `c` (padded) channels: the hi/lo interleave doubles them
+inline int KindPhysCols(int kind, int c) { return kind == kKindBF16X3 ? 2 * c : c; }
 
 // Per-utterance affine u8 quantisation parameters (struct QuantizationParams, src/matrix.h:231-234).
 struct QParam {
@@ -42,7 +49,7 @@ struct UttRows {
 // Rows outside [0, M) read as zero (TMA out-of-bounds fill).
 struct GemmArgs {
   int32_t M, N;
-  int32_t c_pad;                 // multiple of KindTileK(kind)
+  int32_t c_pad;                 // STORED elements per tap and row: multiple of 128 bytes (KindPhysCols)
   int32_t n_taps;
   int32_t tap_off[kMaxTaps];
   int32_t n_pass;                // 1, or 3 for the error-compensated 3xTF32 product
@@ -72,7 +79,8 @@ struct GemmArgs {
   int32_t *out_acc;              // int32 accumulators after the zero-point corrections
   int64_t ld_out;                // row stride (elements) of out_f32 / out_lo / out_bf16 / out_acc
   int32_t n_store;               // columns written per row (>= N; columns [N, n_store) get 0) --
-                                 // the zero padding of the next layer's K dimension
+                                 // the zero padding of the next layer's K dimension.  kKindBF16X3 with
+                                 // out_bf16: logical columns (multiple of 32); ld_out is in stored elements
   int32_t round_tf32;            // out_f32 = tf32-rounded value (so that out_lo is exact)
   int32_t debug;                 // CE_GPU_GEMM_DEBUG bits (timing probes only, results are WRONG):
                                  // 1 = epilogue drains TMEM but skips math and stores,

@@ -213,7 +213,135 @@ int ReadConfigFile(const std::string &path, std::map<std::string, std::string> *
   return rc;
 }
 
-int CompileProgram(const HostNnet &nn, int left_context, int right_context, Program *prog) {
+namespace {
+
+// Any layer list: one step per layer.  The reference's matrices shrink at every NarrowLayer; here
+// the rows stay where they are and the valid range [lo, P - hi) of every utterance block shrinks.
+int CompileGeneral(const HostNnet &nn, int left_context, int right_context, int num_out, Program *prog) {
+  prog->blocks.clear();
+  prog->steps.clear();
+  prog->general = true;
+  prog->log_softmax = false;
+  const int n = (int)nn.layers.size();
+  if (n == 0) {
+    SetError("the nnet has no layers");
+    return CE_GPU_EUNSUPPORTED;
+  }
+  // feature dimension: the first layer that pins a width, divided by the splices in front of it
+  int64_t mult = 1;
+  int feat = 0;
+  for (int i = 0; i < n && feat == 0; ++i) {
+    const HostLayer &L = nn.layers[i];
+    if (L.type == kSplice) mult *= (int64_t)L.indices.size();
+    const int pinned = L.type == kLinear ? L.in_dim : L.type == kBatchNorm ? (int)L.scale.size() : 0;
+    if (pinned > 0) {
+      if (pinned % mult != 0) {
+        SetError("layer %d expects %d inputs, not a multiple of the %lld spliced copies in front of it", i,
+                 pinned, (long long)mult);
+        return CE_GPU_EINVAL;
+      }
+      feat = (int)(pinned / mult);
+    }
+  }
+  if (feat == 0) {
+    if (num_out <= 0 || num_out % mult != 0) {
+      SetError("the nnet has no Linear or BatchNorm layer and the prior (%d entries) does not pin its "
+               "input dimension", num_out);
+      return CE_GPU_EINVAL;
+    }
+    feat = (int)(num_out / mult);
+  }
+  prog->feat_dim = feat;
+  int dim = feat, lo = 0, hi = 0;
+  prog->max_dim = dim;
+  for (int i = 0; i < n; ++i) {
+    const HostLayer &L = nn.layers[i];
+    if (L.type == kLogSoftmax && i == n - 1) {           // fused with the prior subtraction + argmax
+      prog->log_softmax = true;
+      break;
+    }
+    Step st;
+    st.type = L.type;
+    st.layer = i;
+    st.in_dim = dim;
+    st.lo = lo;
+    st.hi = hi;
+    switch (L.type) {
+      case kLinear: {
+        if (L.in_dim != dim) {
+          SetError("layer %d: Linear expects %d inputs, previous layer produces %d", i, L.in_dim, dim);
+          return CE_GPU_EINVAL;
+        }
+        Block b;
+        b.taps.assign(1, 0);
+        b.in_dim = L.in_dim;
+        b.out_dim = L.out_dim;
+        b.linear = i;
+        b.cum_left = lo;
+        b.cum_right = hi;
+        st.block = (int)prog->blocks.size();
+        prog->blocks.push_back(b);
+        dim = L.out_dim;
+        break;
+      }
+      case kSplice:
+        if ((int64_t)dim * (int64_t)L.indices.size() > (1 << 20)) {
+          SetError("layer %d: a spliced row of %lld floats is not supported", i,
+                   (long long)dim * (long long)L.indices.size());
+          return CE_GPU_EUNSUPPORTED;
+        }
+        dim *= (int)L.indices.size();
+        break;
+      case kNarrow:
+        if (L.left < 0 || L.right < 0) {
+          SetError("layer %d: NarrowLayer is not initialized", i);   // nnet.cc:185
+          return CE_GPU_EINVAL;
+        }
+        lo += L.left;
+        hi += L.right;
+        break;
+      case kBatchNorm:
+        if ((int)L.scale.size() != dim) {
+          SetError("layer %d: batch-norm dim %zu != %d", i, L.scale.size(), dim);
+          return CE_GPU_EINVAL;
+        }
+        break;
+      case kReLU: case kNormalize: case kSoftmax: case kLogSoftmax:
+        break;
+      default:
+        SetError("layer %d: unexpected layer type %d", i, L.type);
+        return CE_GPU_EUNSUPPORTED;
+    }
+    st.out_dim = dim;
+    prog->max_dim = std::max(prog->max_dim, dim);
+    prog->steps.push_back(st);
+  }
+  if (lo != left_context || hi != right_context) {
+    // The reference would abort on assert(rows == batch_size), src/am.cc:106.
+    SetError("left/right context %d/%d does not match the rows the nnet removes (%d/%d)",
+             left_context, right_context, lo, hi);
+    return CE_GPU_EINVAL;
+  }
+  prog->num_pdfs = dim;
+  return CE_GPU_OK;
+}
+
+int CompileFused(const HostNnet &nn, int left_context, int right_context, Program *prog);
+
+}  // namespace
+
+int CompileProgram(const HostNnet &nn, int left_context, int right_context, Program *prog, int num_out) {
+  const int rc = CompileFused(nn, left_context, right_context, prog);
+  if (rc != CE_GPU_EUNSUPPORTED) return rc;
+  ClearError();
+  return CompileGeneral(nn, left_context, right_context, num_out, prog);
+}
+
+namespace {
+
+int CompileFused(const HostNnet &nn, int left_context, int right_context, Program *prog) {
+  prog->general = false;
+  prog->steps.clear();
   prog->blocks.clear();
   prog->log_softmax = false;
   const int n = (int)nn.layers.size();
@@ -306,6 +434,8 @@ int CompileProgram(const HostNnet &nn, int left_context, int right_context, Prog
   prog->num_pdfs = dim;
   return CE_GPU_OK;
 }
+
+}  // namespace
 
 void QuantizeHost(const float *src, int64_t count, uint8_t *dst, float *scale_out,
                   int32_t *zp_out) {

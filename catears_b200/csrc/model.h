@@ -54,16 +54,35 @@ struct Block {
                                       // [cum_left, P - cum_right)
 };
 
+// One step of the GENERAL program: layer `layer` of the HostNnet, evaluated on its own (Linear
+// layers still run on the tensor cores, everything else as a row-wise kernel, layers.cu).
+struct Step {
+  int type = -1;                      // LayerType
+  int layer = -1;                     // index into HostNnet::layers
+  int block = -1;                     // Linear: index into Program::blocks
+  int in_dim = 0, out_dim = 0;
+  int lo = 0, hi = 0;                 // valid rows of an utterance block BEFORE this step: [lo, P - hi)
+};
+
 struct Program {
   std::vector<Block> blocks;
   bool log_softmax = false;           // trailing LogSoftmaxLayer
   int feat_dim = 0;
   int num_pdfs = 0;
+  // general == false: `blocks` is the whole network as fused [Splice+Narrow+]Linear[+ReLU][+BN]
+  // steps (the pattern tool/convert_am.py emits).  general == true: any layer list of
+  // src/nnet.h:21-30 in `steps`, one kernel per layer; `blocks` then holds the bare Linear layers.
+  bool general = false;
+  std::vector<Step> steps;
+  int max_dim = 0;                    // widest activation row of the general program
 };
 
-// Matches the layer list against the pattern tool/convert_am.py emits.  Anything
-// else (Normalize / Softmax layers, a Splice without its Narrow, ...) is CE_GPU_EUNSUPPORTED.
-int CompileProgram(const HostNnet &nn, int left_context, int right_context, Program *prog);
+// Matches the layer list against the pattern tool/convert_am.py emits; any other
+// stack (Normalize / Softmax layers, a Splice without its Narrow, ...) compiles to the general
+// program.  num_out: the prior's length (pins the feature dimension of stacks without a Linear or
+// BatchNorm layer; 0 = unknown).
+int CompileProgram(const HostNnet &nn, int left_context, int right_context, Program *prog,
+                   int num_out = 0);
 
 // Quantize (src/matrix.cc:329-387) on the host, for weights at load time.
 void QuantizeHost(const float *src, int64_t count, uint8_t *dst, float *scale, int32_t *zero_point);

@@ -100,6 +100,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     case CE_GPU_PRECISION_BF16: m->kind = kKindBF16; m->n_pass = 1; break;
     case CE_GPU_PRECISION_FP32: m->kind = kKindTF32; m->n_pass = 3; break;
     case CE_GPU_PRECISION_TF32: m->kind = kKindTF32; m->n_pass = 1; break;
+    case CE_GPU_PRECISION_BF16X3: m->kind = kKindBF16X3; m->n_pass = 1; break;
     default:
       SetError("unknown precision %d", precision);
       return CE_GPU_EINVAL;
@@ -134,7 +135,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     D.meta = B;
     D.c_pad = RoundUp(B.in_dim, tile_k);
     const int n_taps = (int)B.taps.size();
-    D.k_total = (int64_t)n_taps * D.c_pad;
+    D.k_total = (int64_t)n_taps * KindPhysCols(m->kind, D.c_pad);
     const int N = B.out_dim, C = B.in_dim, K = n_taps * C;
     // per-column arrays cover every column the epilogue may touch (the next block's K padding)
     int next_pad = N;
@@ -169,6 +170,22 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
           const float *src = L.W.data() + (size_t)(t * C + c) * N;
           const size_t kk = (size_t)t * D.c_pad + c;
           for (int n = 0; n < N; ++n) packed[(size_t)n * D.k_total + kk] = Bf16Bits(src[n]);
+        }
+      CE_CHECK(Upload(&D.w[0], packed.data(), packed.size() * 2));
+    } else if (m->kind == kKindBF16X3) {                 // per 32 channels: [32 hi | 32 lo]
+      std::vector<uint16_t> packed(elems, 0);
+      for (int t = 0; t < n_taps; ++t)
+        for (int c = 0; c < C; ++c) {
+          const float *src = L.W.data() + (size_t)(t * C + c) * N;
+          const size_t kk = (size_t)t * 2 * D.c_pad + (size_t)(c >> 5) * 64 + (c & 31);
+          for (int n = 0; n < N; ++n) {
+            const uint16_t hb = Bf16Bits(src[n]);
+            uint32_t hw = (uint32_t)hb << 16;
+            float hf;
+            memcpy(&hf, &hw, 4);
+            packed[(size_t)n * D.k_total + kk] = hb;
+            packed[(size_t)n * D.k_total + kk + 32] = Bf16Bits(src[n] - hf);
+          }
         }
       CE_CHECK(Upload(&D.w[0], packed.data(), packed.size() * 2));
     } else {
@@ -313,8 +330,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     CE_CHECK(w->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
     CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
     CE_CHECK(w->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
-  } else if (m->kind == kKindBF16) {
-    for (int i = 0; i < 2; ++i) CE_CHECK(w->act_bf16[i].Reserve(2 * (size_t)M * wmax));
+  } else if (m->kind == kKindBF16 || m->kind == kKindBF16X3) {
+    for (int i = 0; i < 2; ++i)
+      CE_CHECK(w->act_bf16[i].Reserve(2 * (size_t)M * KindPhysCols(m->kind, wmax)));
   } else {
     for (int i = 0; i < 2; ++i) {
       CE_CHECK(w->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
@@ -354,12 +372,16 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   } else if (m->kind == kKindBF16) {
     CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, w->act_bf16[0].as<__nv_bfloat16>(),
                            nullptr, nullptr, s));
+  } else if (m->kind == kKindBF16X3) {
+    CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, nullptr, nullptr, nullptr, s,
+                           w->act_bf16[0].as<__nv_bfloat16>()));
   } else {
     CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, nullptr, w->act_f32[0].as<float>(),
                            m->n_pass == 3 ? w->act_lo[0].as<float>() : nullptr, s));
   }
 
   m->kept_valid = false;
+  m->last_n_utts = n_utts;
   for (int b = 0; b < nb; ++b) {
     const DeviceBlock &D = m->blocks[b];
     const bool last = (b == nb - 1);
@@ -369,7 +391,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     memset(&ops, 0, sizeof(ops));
     a.M = M;
     a.N = D.meta.out_dim;
-    a.c_pad = D.c_pad;
+    a.c_pad = KindPhysCols(m->kind, D.c_pad);
     a.n_taps = (int)D.meta.taps.size();
     for (int t = 0; t < a.n_taps; ++t) a.tap_off[t] = D.meta.taps[t];
     a.n_pass = m->n_pass;
@@ -428,7 +450,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         m->kept_ld = a.ld_out;
         m->kept_valid = true;
       }
-    } else if (m->kind == kKindBF16) {
+    } else if (m->kind == kKindBF16 || m->kind == kKindBF16X3) {
       ops.a[0] = w->act_bf16[b & 1].ptr;
       if (last) {
         a.out_f32 = w->logits.as<float>();
@@ -436,8 +458,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         a.n_store = a.N;
       } else {
         a.out_bf16 = w->act_bf16[(b + 1) & 1].as<__nv_bfloat16>();
-        a.ld_out = next_c;
-        a.n_store = next_c;
+        a.ld_out = KindPhysCols(m->kind, next_c);        // stored elements per row
+        a.n_store = next_c;                              // logical columns
       }
     } else {
       ops.a[0] = w->act_f32[b & 1].ptr;

@@ -101,6 +101,7 @@ struct ce_gpu_model {
   int kept_lo = 0, kept_hi = 0, kept_cols = 0;
   int64_t kept_ld = 0;
   bool kept_valid = false;
+  int last_n_utts = 0;                 // utterances of the last chunk evaluated (ce_gpu_nnet_get_qparams)
 
   ~ce_gpu_model();
 };

@@ -330,11 +330,12 @@ __device__ __forceinline__ float RoundTf32(float v) {
   return __uint_as_float(r);
 }
 
-// x [M x ld_in] fp32 (C columns) -> zero-padded [M x c_pad] bf16, or fp32 hi (+ lo).
+// x [M x ld_in] fp32 (C columns) -> zero-padded [M x c_pad] bf16, or fp32 hi (+ lo), or the
+// interleaved bf16 hi/lo operand of kKindBF16X3 ([M x 2 c_pad]: per 32 channels [32 hi | 32 lo]).
 __global__ void __launch_bounds__(256)
 convert_kernel(const float *__restrict__ x, int64_t ld_in, int C, int64_t M, int c_pad,
                __nv_bfloat16 *__restrict__ out_bf16, float *__restrict__ out_hi,
-               float *__restrict__ out_lo) {
+               float *__restrict__ out_lo, __nv_bfloat16 *__restrict__ out_x3) {
   const int64_t n = M * c_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -342,6 +343,12 @@ convert_kernel(const float *__restrict__ x, int64_t ld_in, int C, int64_t M, int
     const int c = (int)(i % c_pad);
     const float v = (c < C) ? x[row * ld_in + c] : 0.0f;
     if (out_bf16) out_bf16[i] = __float2bfloat16_rn(v);
+    if (out_x3) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      __nv_bfloat16 *o = out_x3 + row * (2 * (int64_t)c_pad) + (c >> 5) * 64 + (c & 31);
+      o[0] = h;
+      o[32] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
     if (out_hi) {
       const float h = RoundTf32(v);
       out_hi[i] = h;
@@ -891,12 +898,13 @@ int QuantSelfTestLaunch(int64_t n, uint64_t seed, unsigned long long *mismatches
 }
 
 int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
-                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s) {
+                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s,
+                  __nv_bfloat16 *out_x3) {
   if (M <= 0) return CE_GPU_OK;
   const int64_t n = M * c_pad;
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
   ProfScope prof(kProfOther, s);
-  convert_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, out_bf16, out_hi, out_lo);
+  convert_kernel<<<grid, 256, 0, s>>>(x, ld_in, C, M, c_pad, out_bf16, out_hi, out_lo, out_x3);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

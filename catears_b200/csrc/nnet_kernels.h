@@ -29,7 +29,8 @@ int QuantizeLaunch(const float *x, int64_t ld_in, int C, int M, int c_pad, const
 // pseudo-random (value, scale, zero point) triples (adds to *mismatches_dev).
 int QuantSelfTestLaunch(int64_t n, uint64_t seed, unsigned long long *mismatches_dev, cudaStream_t s);
 int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
-                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s);
+                  __nv_bfloat16 *out_bf16, float *out_hi, float *out_lo, cudaStream_t s,
+                  __nv_bfloat16 *out_x3 = nullptr);
 // What a finished log-likelihood row is written as (include/ce_gpu.h, ce_gpu_model_set_output):
 // all N columns, the columns ids[0..n) (device array), or the n best (loglik, pdf) pairs.
 enum { kOutDense = 0, kOutSubset = 1, kOutTopK = 2 };

@@ -57,9 +57,11 @@ extern "C" {
 
 /* Arithmetic of the Linear layers. */
 #define CE_GPU_PRECISION_INT8 0  /* u8 x u8 -> s32, gemmlowp-compatible (bit-exact accumulators) */
-#define CE_GPU_PRECISION_BF16 1  /* bf16 x bf16 -> fp32                         */
+#define CE_GPU_PRECISION_BF16 1  /* bf16 x bf16 -> fp32 (fast mode, OUTSIDE the 1e-3 log-likelihood bar) */
 #define CE_GPU_PRECISION_FP32 2  /* 3xTF32 error-compensated, fp32-class accuracy */
-#define CE_GPU_PRECISION_TF32 3  /* single-pass TF32                            */
+#define CE_GPU_PRECISION_TF32 3  /* single-pass TF32 (fast mode, OUTSIDE the 1e-3 log-likelihood bar) */
+#define CE_GPU_PRECISION_BF16X3 4 /* bf16 hi/lo operands, 3 products: 16-bit mantissa at the bf16 tensor
+                                     rate; meets the 1e-3 bar (the fast in-tolerance float path)    */
 
 typedef struct ce_gpu_model ce_gpu_model_t;
 
@@ -221,6 +223,12 @@ int ce_gpu_nnet_keep_acc(ce_gpu_model_t *m, int linear_ordinal);
 int ce_gpu_nnet_get_acc(ce_gpu_model_t *m, int utt, int32_t *acc, int64_t cap, int *rows,
                         int *cols);
 
+/* Debug/parity hook (int8 models): the activation (scale, zero_point) that the Quantize in front of
+ * every Linear layer (src/matrix.cc:348-387) produced for utterance `utt` of the last forward call
+ * (which must have fitted one chunk).  scale/zero_point: HOST arrays of `cap` entries.  Returns the
+ * number of Linear layers or a negative error. */
+int ce_gpu_nnet_get_qparams(ce_gpu_model_t *m, int utt, float *scale, int32_t *zero_point, int cap);
+
 /* ---- matrix-level entry points --------------------------------------------- */
 
 /* Quantize (src/matrix.cc:366-387) of a contiguous [rows x cols] fp32 matrix to u8 with one
@@ -242,7 +250,7 @@ int ce_gpu_gemm_u8(const uint8_t *a, float scale_a, int32_t zp_a, const uint8_t 
                    float scale_b, int32_t zp_b, int m, int n, int k, float *c, int32_t *acc,
                    int device, void *stream);
 
-/* C[m x n] = A[m x k] * B[k x n], fp32 in/out, `precision` one of BF16/FP32/TF32 (tensor-core
+/* C[m x n] = A[m x k] * B[k x n], fp32 in/out, `precision` one of BF16/FP32/TF32/BF16X3 (tensor-core
  * replacement for MatMat / cblas_sgemm, src/matrix.cc:300-323). */
 int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *c,
                     int precision, int device, void *stream);

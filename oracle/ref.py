@@ -75,6 +75,11 @@ class Ref:
                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
                                      C.c_void_p, C.c_long, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int)]
+        if hasattr(L, "ref_u8_forward_trace"):
+            L.ref_u8_forward_trace.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, C.c_long,
+                                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_set_sgemm_backend.argtypes = [C.c_int, C.c_char_p]
         self.mel = L.ref_fbank_dim()
 
@@ -208,5 +213,40 @@ class Ref:
             if acc is not None:
                 acc = acc[: ar.value * ac.value].reshape(ar.value, ac.value).copy()
             return y, acc
+        finally:
+            self.L.ref_u8_close(h)
+
+    def u8_forward_trace(self, nnet_path, prior_path, left, right, feats, want_acc=True,
+                         out_cols_max=8192, max_layers=64):
+        """int8 composition with every Linear layer traced: returns (loglik, [(scale, zero_point)],
+        [acc per Linear layer] or None)."""
+        h = self.L.ref_u8_open(nnet_path.encode(), prior_path.encode(), left, right)
+        if not h:
+            raise RuntimeError("ref_u8_open failed")
+        try:
+            feats = np.ascontiguousarray(feats, np.float32)
+            T = feats.shape[0]
+            rows = T + left + right
+            cap = rows * out_cols_max
+            out = np.zeros(cap, np.float32)
+            r, c = C.c_int(), C.c_int()
+            sc = np.zeros(max_layers, np.float32)
+            zp = np.zeros(max_layers, np.int32)
+            off = np.zeros(max_layers + 1, np.int64)
+            ar = np.zeros(max_layers, np.int32)
+            ac = np.zeros(max_layers, np.int32)
+            acc_cap = rows * out_cols_max * 3 if want_acc else 0
+            acc = np.zeros(acc_cap, np.int32) if want_acc else None
+            n = self.L.ref_u8_forward_trace(h, feats, T, feats.shape[1], out, cap, C.byref(r),
+                                            C.byref(c), max_layers, sc.ctypes.data, zp.ctypes.data,
+                                            acc.ctypes.data if want_acc else None, acc_cap,
+                                            off.ctypes.data, ar.ctypes.data, ac.ctypes.data)
+            if n < 0:
+                raise RuntimeError("ref_u8_forward_trace: %d" % n)
+            y = out[: r.value * c.value].reshape(r.value, c.value).copy()
+            accs = None
+            if want_acc:
+                accs = [acc[off[i]:off[i + 1]].reshape(ar[i], ac[i]).copy() for i in range(n)]
+            return y, list(zip(sc[:n].tolist(), zp[:n].tolist())), accs
         finally:
             self.L.ref_u8_close(h)

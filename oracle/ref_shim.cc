@@ -409,12 +409,22 @@ void ref_u8_close(void *h) { delete static_cast<U8Model *>(h); }
 // One utterance as ONE batch: replicate-pad left/right rows as
 // am.cc:119-124,152-155, propagate, subtract the log prior (am.cc:109-112).
 // `dump_layer` >= 0: also return that Linear layer's (ordinal among Linear
-// layers) int32 accumulators [rows x out] in acc_out and its dims.
-int ref_u8_forward(void *h, const float *feats, int T, int dim, float *out,
-                   long cap, int *out_rows, int *out_cols, int dump_layer,
-                   int32_t *acc_out, long acc_cap, int *acc_rows,
-                   int *acc_cols) {
-  U8Model *model = static_cast<U8Model *>(h);
+// layers) int32 accumulators [rows x out] in acc_out and its dims; dump_layer == -2 with a trace:
+// the accumulators of EVERY Linear layer, concatenated (acc_off[i] = first element of layer i), and
+// the activation QuantizationParams each Linear layer's Quantize produced.
+struct U8Trace {
+  int cap_layers;
+  int n_layers;
+  float *q_scale;
+  int32_t *q_zp;
+  long *acc_off;      // [cap_layers + 1]
+  int *acc_rows, *acc_cols;
+};
+
+static int U8Forward(U8Model *model, const float *feats, int T, int dim, float *out,
+                     long cap, int *out_rows, int *out_cols, int dump_layer,
+                     int32_t *acc_out, long acc_cap, int *acc_rows, int *acc_cols,
+                     U8Trace *trace) {
   int rows = T + model->left + model->right;
   Matrix<float> cur(rows, dim), next;
   for (int r = 0; r < rows; ++r) {
@@ -424,6 +434,7 @@ int ref_u8_forward(void *h, const float *feats, int T, int dim, float *out,
     memcpy(cur.Row(r).Data(), feats + (size_t)src * dim, sizeof(float) * dim);
   }
   int linear_ordinal = 0;
+  long acc_used = 0;
   if (acc_rows) *acc_rows = 0;
   if (acc_cols) *acc_cols = 0;
   for (U8Layer &L : model->layers) {
@@ -439,6 +450,23 @@ int ref_u8_forward(void *h, const float *feats, int T, int dim, float *out,
                       next.NumRows(), next.NumCols(), in8.NumCols(), acc_out);
         *acc_rows = next.NumRows();
         *acc_cols = next.NumCols();
+      }
+      if (trace != nullptr) {
+        if (linear_ordinal >= trace->cap_layers) return -3;
+        trace->q_scale[linear_ordinal] = qa.scale;
+        trace->q_zp[linear_ordinal] = qa.zero_point;
+        trace->acc_off[linear_ordinal] = acc_used;
+        trace->acc_rows[linear_ordinal] = next.NumRows();
+        trace->acc_cols[linear_ordinal] = next.NumCols();
+        if (acc_out != nullptr) {
+          const long n = (long)next.NumRows() * next.NumCols();
+          if (acc_used + n > acc_cap) return -2;
+          GemmlowpInt32(in8.Data(), qa.zero_point, L.W8.Data(), L.qW.zero_point,
+                        next.NumRows(), next.NumCols(), in8.NumCols(), acc_out + acc_used);
+          acc_used += n;
+        }
+        trace->acc_off[linear_ordinal + 1] = acc_used;
+        trace->n_layers = linear_ordinal + 1;
       }
       for (int r = 0; r < next.NumRows(); ++r) {
         SubVector<float> row = next.Row(r);
@@ -461,6 +489,26 @@ int ref_u8_forward(void *h, const float *feats, int T, int dim, float *out,
     memcpy(out + (size_t)r * cur.NumCols(), cur.Row(r).Data(),
            sizeof(float) * cur.NumCols());
   return 0;
+}
+
+int ref_u8_forward(void *h, const float *feats, int T, int dim, float *out,
+                   long cap, int *out_rows, int *out_cols, int dump_layer,
+                   int32_t *acc_out, long acc_cap, int *acc_rows,
+                   int *acc_cols) {
+  return U8Forward(static_cast<U8Model *>(h), feats, T, dim, out, cap, out_rows, out_cols,
+                   dump_layer, acc_out, acc_cap, acc_rows, acc_cols, nullptr);
+}
+
+// Every Linear layer in one pass: activation quantisation parameters and (acc_all nullable) the
+// int32 accumulators of all of them.  Returns the number of Linear layers (>= 0) or an error (< 0).
+int ref_u8_forward_trace(void *h, const float *feats, int T, int dim, float *out, long cap,
+                         int *out_rows, int *out_cols, int cap_layers, float *q_scale,
+                         int32_t *q_zp, int32_t *acc_all, long acc_cap, long *acc_off,
+                         int *acc_rows, int *acc_cols) {
+  U8Trace t = {cap_layers, 0, q_scale, q_zp, acc_off, acc_rows, acc_cols};
+  int rc = U8Forward(static_cast<U8Model *>(h), feats, T, dim, out, cap, out_rows, out_cols, -2,
+                     acc_all, acc_cap, nullptr, nullptr, &t);
+  return rc < 0 ? rc : t.n_layers;
 }
 
 }  // extern "C"
