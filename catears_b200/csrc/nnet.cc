@@ -10,6 +10,8 @@
 // are the reference's rows; the others hold values that no valid row ever reads.
 #include "nnet.h"
 
+#include "layers.h"
+
 #include <math.h>
 #include <string.h>
 
@@ -36,6 +38,7 @@ ce_gpu_model::~ce_gpu_model() {
   for (auto &b : blocks) {
     b.w[0].Free(); b.w[1].Free(); b.bias.Free(); b.bn_scale.Free(); b.bn_offset.Free(); b.colsum.Free();
   }
+  for (auto &g : gen) { g.idx.Free(); g.scale.Free(); g.offset.Free(); }
   log_prior.Free(); cmvn_dev.Free(); out_ids.Free();
   stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
   stage_argmax_all.Free();
@@ -105,7 +108,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
       SetError("unknown precision %d", precision);
       return CE_GPU_EINVAL;
   }
-  CE_CHECK(CompileProgram(nn, left, right, &m->prog));
+  CE_CHECK(CompileProgram(nn, left, right, &m->prog, (int)prior.size()));
   if ((int)prior.size() != m->prog.num_pdfs) {
     SetError("prior has %zu entries, the nnet has %d outputs", prior.size(), m->prog.num_pdfs);
     return CE_GPU_EINVAL;
@@ -205,6 +208,16 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
       if (m->n_pass == 3) CE_CHECK(Upload(&D.w[1], lo.data(), lo.size() * 4));
     }
   }
+  m->gen.resize(m->prog.steps.size());
+  for (size_t i = 0; i < m->prog.steps.size(); ++i) {
+    const Step &st = m->prog.steps[i];
+    const HostLayer &L = nn.layers[st.layer];
+    if (st.type == kSplice) CE_CHECK(Upload(&m->gen[i].idx, L.indices.data(), sizeof(int32_t) * L.indices.size()));
+    if (st.type == kBatchNorm) {
+      CE_CHECK(Upload(&m->gen[i].scale, L.scale.data(), sizeof(float) * L.scale.size()));
+      CE_CHECK(Upload(&m->gen[i].offset, L.offset.data(), sizeof(float) * L.offset.size()));
+    }
+  }
   if (const char *e = getenv("CE_GPU_CHUNK_ROWS")) {
     long v = atol(e);
     if (v >= kTileM) m->max_chunk_rows = v;
@@ -256,14 +269,19 @@ struct PcmSource {
   const int64_t *sample_off = nullptr;  // [n_utts + 1] of this chunk
 };
 
-// s: stream of the memory-bound kernels; s_gemm: stream of the GEMMs (== s when chunks are not
-// overlapped).
-int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
-                 const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
-                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s, cudaStream_t s_gemm) {
-  const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
-  const int nb = (int)m->blocks.size();
+// The row space of one chunk (see the header comment) and its tables on the device.
+struct RowSpace {
+  int M = 0;                            // rows, a multiple of kTileM
+  bool gran = false;                    // blocks at multiples of kRowGran instead of kTileM
+  std::vector<int64_t> row_off64;       // first row of every utterance block
+  const UttRows *d_utts = nullptr;
+  const int32_t *d_tile = nullptr;
+  const UttRows *h_utts = nullptr;
+};
 
+int BuildRowSpace(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const int64_t *frame_off, int n_utts,
+                  cudaStream_t s, RowSpace *rs) {
+  const int L = m->left, R = m->right;
   // ---- row space ----
   // Every utterance block starts at a multiple of kTileM rows (one utterance per GEMM tile).  When
   // the blocks are short -- micro-batches of live streams, a few frames plus context each -- that
@@ -289,7 +307,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   }
   const int64_t m_used = M64;
   M64 = (M64 + kTileM - 1) / kTileM * kTileM;            // whole GEMM tiles; the tail belongs to nobody
-  if (M64 == 0) return CE_GPU_OK;
+  if (M64 == 0) return CE_GPU_OK;                      // rs->M stays 0
   if (M64 > 0x7fffff00LL) {
     SetError("a chunk of %lld rows exceeds the 2^31 row limit", (long long)M64);
     return CE_GPU_EINVAL;
@@ -318,6 +336,218 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   const UttRows *d_utts = w->utt_table.dev<UttRows>();
   const int32_t *d_tile = w->tile_table.dev<int32_t>();
 
+  rs->M = M;
+  rs->gran = gran;
+  rs->row_off64.swap(row_off64);
+  rs->d_utts = d_utts;
+  rs->d_tile = d_tile;
+  rs->h_utts = hu;
+  return CE_GPU_OK;
+}
+
+// fbank of the chunk's utterances (when the input is PCM) + replicate padding (+ CMVN) into x0
+// (src/am.cc:119-124,152-155).  For the u8 path the same kernel reduces each utterance's min/max (the
+// padding rows are copies, so the frames' min/max is the matrix's) for the first Quantize.
+int ChunkInput(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src, const float *feats_dev,
+               const int64_t *frame_off, int n_utts, bool apply_cmvn, const RowSpace &rs, uint32_t *mm_first,
+               cudaStream_t s) {
+  const int L = m->left, R = m->right, F = m->prog.feat_dim;
+  std::vector<int64_t> local_off;
+  const int64_t *feat_off = frame_off;
+  if (src.pcm_dev) {
+    local_off.resize(n_utts + 1);
+    for (int u = 0; u <= n_utts; ++u) local_off[u] = frame_off[u] - frame_off[0];
+    CE_CHECK(w->feats.Reserve(sizeof(float) * (size_t)local_off[n_utts] * F));
+    CE_CHECK(FbankLaunch(src.pcm_dev, src.total_samples, src.sample_off, local_off.data(), n_utts, F,
+                         w->feats.as<float>(), F, &w->fbank_chunks, s));
+    feats_dev = w->feats.as<float>();
+    feat_off = local_off.data();
+  }
+  return CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr, apply_cmvn ? m->cmvn_host[F] : 0.0f,
+                    feats_dev, feat_off, rs.row_off64.data(), n_utts, F, L, R, w->x0.as<float>(), F,
+                    &w->cmvn_utts, s, nullptr, mm_first);
+}
+
+// The general layer program (Program::general): any layer list of src/nnet.h:21-30, one kernel per
+// layer over fp32 activations in the padded row space.  Linear layers run on the tensor cores in the
+// model's precision -- for int8 that is Quantize(in) + MatMat_U8U8F32 + AddVec(b) per Linear layer,
+// the composition of SURVEY D3 -- everything else as the row-wise kernels of layers.cu.
+int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
+                        const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
+                        float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
+  const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
+  const int nb = (int)m->blocks.size();
+  RowSpace rs;
+  CE_CHECK(BuildRowSpace(m, w, frame_off, n_utts, s, &rs));
+  if (rs.M == 0) return CE_GPU_OK;
+  const int M = rs.M;
+  const int wmax = RoundUp(std::max(m->prog.max_dim, 4), 4);
+  int cmax = 4;
+  for (const DeviceBlock &D : m->blocks) cmax = std::max(cmax, D.c_pad);
+  CE_CHECK(w->x0.Reserve(sizeof(float) * (size_t)M * F));
+  for (int i = 0; i < 2; ++i) CE_CHECK(w->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
+  if (nb > 0) {
+    if (m->kind == kKindI8) {
+      CE_CHECK(w->act_u8.Reserve((size_t)M * cmax));
+      CE_CHECK(w->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
+      CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
+      CE_CHECK(w->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
+      CE_CHECK(InitMinMaxLaunch(w->minmax.as<uint32_t>(), nb * n_utts, s));
+    } else if (m->kind == kKindBF16 || m->kind == kKindBF16X3) {
+      CE_CHECK(w->act_bf16[0].Reserve(2 * (size_t)M * KindPhysCols(m->kind, cmax)));
+    } else {
+      CE_CHECK(w->act_lo[0].Reserve(sizeof(float) * (size_t)M * cmax));   // operand hi
+      if (m->n_pass == 3) CE_CHECK(w->act_lo[1].Reserve(sizeof(float) * (size_t)M * cmax));
+    }
+  }
+  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, nullptr, s));
+
+  m->kept_valid = false;
+  m->last_n_utts = n_utts;
+  float *cur = w->x0.as<float>();
+  int64_t ld = F;
+  int dim = F, which = 0;                                // act_f32[which] is the next free buffer
+  for (const Step &st : m->prog.steps) {
+    const ce::GenStepDev &G = m->gen[&st - m->prog.steps.data()];
+    switch (st.type) {
+      case kNarrow:                                      // only the valid range shrinks (st.lo / st.hi)
+        break;
+      case kSplice: {
+        float *out = w->act_f32[which].as<float>();
+        CE_CHECK(SpliceLaunch(cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi, G.idx.as<int32_t>(),
+                              st.out_dim / std::max(1, st.in_dim), out, RoundUp(st.out_dim, 4), s));
+        cur = out;
+        ld = RoundUp(st.out_dim, 4);
+        which ^= 1;
+        break;
+      }
+      case kReLU:
+        CE_CHECK(RowwiseLaunch(kRowReLU, cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi, nullptr, nullptr, s));
+        break;
+      case kBatchNorm:
+        CE_CHECK(RowwiseLaunch(kRowBatchNorm, cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi,
+                               G.scale.as<float>(), G.offset.as<float>(), s));
+        break;
+      case kNormalize:
+        CE_CHECK(RowwiseLaunch(kRowNormalize, cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi, nullptr, nullptr, s));
+        break;
+      case kSoftmax:
+        CE_CHECK(RowwiseLaunch(kRowSoftmax, cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi, nullptr, nullptr, s));
+        break;
+      case kLogSoftmax:
+        CE_CHECK(RowwiseLaunch(kRowLogSoftmax, cur, ld, dim, M, rs.d_tile, rs.d_utts, st.lo, st.hi, nullptr, nullptr, s));
+        break;
+      case kLinear: {
+        const int b = st.block;
+        const DeviceBlock &D = m->blocks[b];
+        GemmArgs a;
+        memset(&a, 0, sizeof(a));
+        GemmOperands ops;
+        memset(&ops, 0, sizeof(ops));
+        a.M = M;
+        a.N = D.meta.out_dim;
+        a.c_pad = KindPhysCols(m->kind, D.c_pad);
+        a.n_taps = 1;
+        a.n_pass = m->n_pass;
+        if (m->n_pass == 3) {
+          a.pass_a[0] = 1; a.pass_b[0] = 0;
+          a.pass_a[1] = 0; a.pass_b[1] = 1;
+          a.pass_a[2] = 0; a.pass_b[2] = 0;
+        }
+        a.bias = D.bias.as<float>();
+        a.tile_utt = rs.d_tile;
+        a.gran = rs.gran ? 1 : 0;
+        a.utts = rs.d_utts;
+        ops.rows_a = M;
+        ops.rows_b = D.meta.out_dim;
+        ops.k_total = D.k_total;
+        ops.b[0] = D.w[0].ptr;
+        ops.b[1] = D.w[1].ptr;
+        if (m->kind == kKindI8) {
+          uint32_t *mm = w->minmax.as<uint32_t>() + 2 * (size_t)b * n_utts;
+          QParam *qp = w->qparams.as<QParam>() + (size_t)b * n_utts;
+          RowUse use;
+          memset(&use, 0, sizeof(use));
+          use.lo = st.lo;
+          use.hi = st.hi;
+          CE_CHECK(MinMaxLaunch(cur, ld, dim, M, rs.d_tile, rs.d_utts, use, mm, s));
+          CE_CHECK(QuantizeLaunch(cur, ld, dim, M, D.c_pad, rs.d_tile, mm, n_utts, qp, w->act_u8.as<uint8_t>(),
+                                  w->rowsum.as<int32_t>(), s));
+          ops.a[0] = w->act_u8.ptr;
+          a.a_rowsum = w->rowsum.as<int32_t>();
+          a.b_colsum = D.colsum.as<int32_t>();
+          a.zp_b = D.zp_b;
+          a.scale_b = D.scale_b;
+          a.k_true = D.meta.in_dim;
+          a.qa = qp;
+        } else if (m->kind == kKindBF16) {
+          CE_CHECK(ConvertLaunch(cur, ld, dim, M, D.c_pad, w->act_bf16[0].as<__nv_bfloat16>(), nullptr, nullptr, s));
+          ops.a[0] = w->act_bf16[0].ptr;
+        } else if (m->kind == kKindBF16X3) {
+          CE_CHECK(ConvertLaunch(cur, ld, dim, M, D.c_pad, nullptr, nullptr, nullptr, s,
+                                 w->act_bf16[0].as<__nv_bfloat16>()));
+          ops.a[0] = w->act_bf16[0].ptr;
+        } else {
+          CE_CHECK(ConvertLaunch(cur, ld, dim, M, D.c_pad, nullptr, w->act_lo[0].as<float>(),
+                                 m->n_pass == 3 ? w->act_lo[1].as<float>() : nullptr, s));
+          ops.a[0] = w->act_lo[0].ptr;
+          ops.a[1] = m->n_pass == 3 ? w->act_lo[1].ptr : nullptr;
+        }
+        float *out = w->act_f32[which].as<float>();
+        a.out_f32 = out;
+        a.ld_out = RoundUp(a.N, 4);
+        a.n_store = a.N;
+        if (m->kind == kKindI8 && m->keep_acc == b) {
+          CE_CHECK(m->acc_dump.Reserve(sizeof(int32_t) * (size_t)M * a.ld_out));
+          a.out_acc = m->acc_dump.as<int32_t>();
+          m->kept_row_off.resize(n_utts);
+          m->kept_rows.resize(n_utts);
+          for (int u = 0; u < n_utts; ++u) {
+            m->kept_row_off[u] = rs.h_utts[u].row_off;
+            m->kept_rows[u] = rs.h_utts[u].rows;
+          }
+          m->kept_lo = st.lo;
+          m->kept_hi = st.hi;
+          m->kept_cols = a.N;
+          m->kept_ld = a.ld_out;
+          m->kept_valid = true;
+        }
+        CE_CHECK(GemmLaunch(m->kind, ops, a, s));
+        cur = out;
+        ld = a.ld_out;
+        which ^= 1;
+        break;
+      }
+      default:
+        SetError("general program: unexpected layer type %d", st.type);
+        return CE_GPU_EUNSUPPORTED;
+    }
+    dim = st.out_dim;
+  }
+  return FinalizeLaunch(cur, ld, NP, M, rs.d_tile, rs.d_utts, w->outrow_table.dev<int64_t>(), L, R,
+                        m->prog.log_softmax, m->log_prior.as<float>(), loglik_dev, m->out_words(), argmax_dev,
+                        s, m->out_sel);
+}
+
+// s: stream of the memory-bound kernels; s_gemm: stream of the GEMMs (== s when chunks are not
+// overlapped).
+int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
+                 const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
+                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s, cudaStream_t s_gemm) {
+  const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
+  const int nb = (int)m->blocks.size();
+
+  if (m->prog.general)
+    return ForwardChunkGeneral(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, loglik_dev, argmax_dev, s);
+  RowSpace rs;
+  CE_CHECK(BuildRowSpace(m, w, frame_off, n_utts, s, &rs));
+  if (rs.M == 0) return CE_GPU_OK;
+  const int M = rs.M;
+  const bool gran = rs.gran;
+  const UttRows *d_utts = rs.d_utts;
+  const int32_t *d_tile = rs.d_tile;
+  const UttRows *hu = rs.h_utts;
+
   // ---- workspace ----
   int wmax = 4;
   for (const DeviceBlock &D : m->blocks) wmax = std::max(wmax, std::max(D.c_pad, RoundUp(D.meta.out_dim, 4)));
@@ -340,29 +570,11 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     }
   }
 
-  // ---- fbank of this chunk's utterances (when the input is PCM) ----
-  std::vector<int64_t> local_off;
-  const int64_t *feat_off = frame_off;
-  if (src.pcm_dev) {
-    local_off.resize(n_utts + 1);
-    for (int u = 0; u <= n_utts; ++u) local_off[u] = frame_off[u] - frame_off[0];
-    CE_CHECK(w->feats.Reserve(sizeof(float) * (size_t)local_off[n_utts] * F));
-    CE_CHECK(FbankLaunch(src.pcm_dev, src.total_samples, src.sample_off, local_off.data(), n_utts, F,
-                         w->feats.as<float>(), F, &w->fbank_chunks, s));
-    feats_dev = w->feats.as<float>();
-    feat_off = local_off.data();
-  }
-
-  // ---- replicate padding (+ CMVN) into x0: src/am.cc:119-124,152-155.  For the u8 path the same
-  // kernel reduces each utterance's min/max (the padding rows are copies, so the frames' min/max is
-  // the matrix's) for the first Quantize. ----
+  // ---- fbank (when the input is PCM), replicate padding (+ CMVN) into x0, first min/max ----
   uint32_t *mm = w->minmax.as<uint32_t>();
   QParam *qp = w->qparams.as<QParam>();
   if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
-  CE_CHECK(CmvnLaunch(apply_cmvn ? m->cmvn_dev.as<float>() : nullptr,
-                      apply_cmvn ? m->cmvn_host[F] : 0.0f, feats_dev, feat_off, row_off64.data(),
-                      n_utts, F, L, R, w->x0.as<float>(), F, &w->cmvn_utts, s, nullptr,
-                      m->kind == kKindI8 ? mm : nullptr));
+  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, m->kind == kKindI8 ? mm : nullptr, s));
 
   // ---- network input in the operand format of the data path ----
   const int c0 = m->blocks[0].c_pad;

@@ -22,6 +22,12 @@ struct DeviceBlock {
   int32_t zp_b = 0;
 };
 
+// Device-side parameters of one step of the general program (Program::steps).
+struct GenStepDev {
+  DevBuf idx;                // Splice indices
+  DevBuf scale, offset;      // BatchNorm
+};
+
 }  // namespace ce
 
 // The opaque handle of include/ce_gpu.h.
@@ -33,6 +39,7 @@ struct ce_gpu_model {
   int left = 0, right = 0;
   ce::Program prog;
   std::vector<ce::DeviceBlock> blocks;
+  std::vector<ce::GenStepDev> gen;     // general program only: one entry per Program::steps entry
   ce::DevBuf log_prior;      // log(prior), src/am.cc:43-44
   bool has_cmvn = false;
   std::vector<float> cmvn_host;   // num_mel sums + count

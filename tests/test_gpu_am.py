@@ -167,14 +167,27 @@ def test_no_logsoftmax_and_plain_linear_stack(port, tmp_path):
     m.close()
 
 
-def test_unsupported_stack_is_reported(tmp_path):
+def test_splice_without_narrow_runs_as_general_program(tmp_path, port):
+    """A Splice that is not followed by its Narrow (not the tool/convert_am.py pattern) no longer is
+    CE_GPU_EUNSUPPORTED: it compiles to the general layer program (edge clamp of src/nnet.cc:64-66).
+    With contexts the stack does not remove, loading fails like the reference's assert (am.cc:106)."""
+    rng = np.random.default_rng(32)
     layers = [{"type": F.SPLICE, "indices": [-1, 0, 1]},
-              {"type": F.LINEAR, "W": np.zeros((120, 8), np.float32), "b": np.zeros(8, np.float32)}]
+              {"type": F.LINEAR, "W": rng.standard_normal((120, 8)).astype(np.float32),
+               "b": rng.standard_normal(8).astype(np.float32)}]
     nnet, prior = str(tmp_path / "u.nnet"), str(tmp_path / "u.prior")
-    F.write_nnet(nnet, layers, 1, 1)
-    F.write_vector(prior, np.full(8, 0.125, np.float32))
-    with pytest.raises(api.CeGpuError, match="Splice must be followed"):
+    F.write_nnet(nnet, layers, 0, 0)
+    pr = np.full(8, 0.125, np.float32)
+    F.write_vector(prior, pr)
+    with pytest.raises(api.CeGpuError, match="does not match the rows the nnet removes"):
         api.AcousticModelGpu(nnet=nnet, prior=prior, left_context=1, right_context=1)
+    x = rng.standard_normal((9, 40)).astype(np.float32)
+    m = api.AcousticModelGpu(nnet=nnet, prior=prior, precision="fp32")
+    ll, _ = m.nnet(x)
+    m.close()
+    idx = np.clip(np.arange(9)[:, None] + np.array([-1, 0, 1])[None, :], 0, 8)
+    want = x[idx].reshape(9, 120).astype(np.float64) @ layers[1]["W"].astype(np.float64) + layers[1]["b"]
+    assert np.abs(ll - (want - np.log(pr))).max() < 1e-3
 
 
 def test_two_handles_two_threads_concurrently(small_model, port):
