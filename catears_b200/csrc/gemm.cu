@@ -285,7 +285,11 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
         x = __uint_as_float(raw[j]);
       }
       x = __fadd_rn(x, bv[e]);                                         // nnet.cc:34
-      if (RELU) x = (x < 0.0f) ? 0.0f : x;                             // nnet.cc:156
+      if (RELU) {
+        // nnet.cc:156 `if (x < 0) x = 0`: a NaN stays a NaN, which is max.NaN (one instruction instead of
+        // compare + select; -0.0 becomes +0.0, equal under every comparison the path makes)
+        asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(x) : "f"(x));
+      }
       if (BN) {
         x = __fmul_rn(x, sv[e]);                                       // nnet.cc:114
         x = __fadd_rn(x, ov[e]);                                       // nnet.cc:115
@@ -656,7 +660,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         } else {
           float h[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) h[j] = p.round_tf32 ? round_tf32(v[j]) : v[j];
+          for (int j = 0; j < 32; ++j) h[j] = (KIND == kKindTF32 && p.round_tf32) ? round_tf32(v[j]) : v[j];
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
 #pragma unroll
@@ -667,7 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           fence_async_smem();
           __syncwarp();
           if (lane == 0) tma_store_2d(&map_o0, stg_u32, col0, m0 + quad * 32);
-          if (p.out_lo) {                                // 3xTF32 consumers: the exact remainder
+          if (KIND == kKindTF32 && p.out_lo) {           // 3xTF32 consumers: the exact remainder
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
 #pragma unroll
