@@ -66,15 +66,16 @@ def model_dir():
 _W = {}
 
 
-def _cpu_worker_init(conf, kind):
+def _cpu_worker_init(conf, kind, variant=""):
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from catears_b200 import formats as F, synth
     _W["stats"] = synth.default_cmvn_stats()
     _W["kind"] = kind
+    _W["conf"] = conf
     if kind == "reference":
         import ctypes as C
         from oracle import ref as R
-        r = R.Ref()
+        r = R.Ref(variant)
         _W["blas"] = "openblas" if r.set_sgemm("openblas") else "inorder"
         if _W["blas"] == "inorder":
             r.set_sgemm("inorder")
@@ -113,6 +114,31 @@ def _cpu_one_utt(u):
     return time.perf_counter() - t0, _W["blas"]
 
 
+def _cpu_one_utt_int8(args):
+    """The int8 composition (Quantize + MatMat_U8U8F32 + bias per Linear layer, gemmlowp as
+    this build of the reference selects its kernel) on `seconds` of synthetic audio, one core."""
+    u, seconds = args
+    from catears_b200 import synth
+    r = _W["ref"]
+    d = os.path.dirname(_W["conf"])
+    pcm = synth.synth_utterance(u, int(seconds * 16000))
+    import ctypes as C
+    if "u8" not in _W:                                   # model load + weight quantisation: not timed
+        _W["u8"] = r.L.ref_u8_open(os.path.join(d, "tdnn.nnet").encode(), os.path.join(d, "tdnn.prior").encode(),
+                                   13, 13)
+        if not _W["u8"]:
+            raise RuntimeError("ref_u8_open failed")
+    t0 = time.perf_counter()
+    feats = r.cmvn(_W["stats"], r.fbank(pcm))
+    T = feats.shape[0]
+    out = np.zeros((T + 26) * 3072, np.float32)
+    rr, cc = C.c_int(), C.c_int()
+    rc = r.L.ref_u8_forward(_W["u8"], feats, T, feats.shape[1], out, out.size, C.byref(rr), C.byref(cc), -1,
+                            None, 0, None, None)
+    assert rc == 0 and rr.value == T, (rc, rr.value)
+    return time.perf_counter() - t0
+
+
 def _cpu_worker_loop(args):
     """Runs utterances for at least `budget` seconds; returns (n, elapsed, blas)."""
     first, budget = args
@@ -136,9 +162,51 @@ def cpu_kind():
     return "reference" if R.available() else "port"
 
 
-def make_pool(conf, kind, cores):
+def make_pool(conf, kind, cores, variant=""):
     import multiprocessing as mp
-    return mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(conf, kind))
+    return mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init, initargs=(conf, kind, variant))
+
+
+def load_reference_in_parent():
+    """dlopen the reference library in this (parent) process too: the work runs in forked pool workers,
+    and the driver's loaded-library record is taken from the process it started."""
+    from oracle import ref as R
+    if R.available():
+        R.Ref()
+
+
+def cpu_baseline_int8(conf):
+    """BASELINE.md section 4 / SURVEY 8d: the reference's int8 path on the host cores, as shipped
+    (no -msse4.1: gemmlowp's scalar reference kernel) and built with -msse4.1 (its SSE4
+    kernel; integer results identical), one worker per core; plus the float path on ONE core."""
+    from oracle import ref as R
+    out = {}
+    cores = cpu_cores()
+    for key, variant, seconds in (("int8_as_shipped", "", 3.0), ("int8_sse4", "_sse4", 10.0)):
+        if not R.available(variant):
+            continue
+        pool = make_pool(conf, "reference", cores, variant)
+        try:
+            t = pool.map(_cpu_one_utt_int8, [(300000 + i, seconds) for i in range(cores)])
+        finally:
+            pool.close()
+            pool.join()
+        out[key] = {"value": round(sum(seconds / x for x in t), 2), "unit": UNIT, "cores": cores,
+                    "kind": "reference",
+                    "sample": "%d utterances of %.0f s, one per core, Quantize + MatMat_U8U8F32 per Linear layer "
+                              "(gemmlowp %s kernel)" % (cores, seconds, "SSE4" if variant else "scalar reference")}
+    if R.available():
+        pool = make_pool(conf, "reference", 1)
+        try:
+            res = pool.map(_cpu_worker_loop, [(400000, 4.0)])
+        finally:
+            pool.close()
+            pool.join()
+        out["float_single_thread"] = {"value": round(res[0][0] * UTT_SECONDS / res[0][1], 2), "unit": UNIT,
+                                      "cores": 1, "kind": "reference",
+                                      "sample": "%d synthetic 10 s utterances on one core, float AM (cblas_sgemm = %s)"
+                                                % (res[0][0], res[0][2])}
+    return out
 
 
 def cpu_baseline(conf, budget_s=6.0):
@@ -165,6 +233,8 @@ def run_reference(args):
         return
     conf = os.path.join(model_dir(), "tdnn.conf")
     kind, cores = cpu_kind(), cpu_cores()
+    if kind == "reference":
+        load_reference_in_parent()
     pool = make_pool(conf, kind, cores)
     try:
         def step(i):
@@ -256,9 +326,12 @@ def run_gpu(args):
     conf = os.path.join(model_dir(), "tdnn.conf")
 
     # CPU baseline first (fork-based pool must start before CUDA is initialised).
-    base = None
+    base = base_more = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         base = cpu_baseline(conf)
+        if cpu_kind() == "reference":
+            load_reference_in_parent()
+            base_more = cpu_baseline_int8(conf)
 
     import torch
     import torch.distributed as dist
@@ -339,19 +412,21 @@ def run_gpu(args):
     e2e = audio_per_step * args.steps / (ms_e2e * 1e-3)
 
     e2e_ll = None
-    if args.e2e_loglik and world == 1:
+    if not args.no_extra_legs and world == 1:
         h_ll = torch.empty((frames, model.num_pdfs), dtype=torch.float32).pin_memory()
 
         def step_ll():
             model.forward(h_pcm.numpy(), off, loglik=h_ll.numpy(), argmax=h_am.numpy(), stream=stream)
         step_ll()
-        ms_ll = timed(step_ll, max(1, args.steps // 2))
-        e2e_ll = audio_per_step * max(1, args.steps // 2) / (ms_ll * 1e-3)
+        n_ll = max(1, min(2, args.steps))
+        ms_ll = timed(step_ll, n_ll)
+        e2e_ll = audio_per_step * n_ll / (ms_ll * 1e-3)
+        del h_ll
 
     # The same with the k best (loglik, pdf) pairs per frame instead of the dense row (SURVEY 8f
     # rank 4): 8 k bytes a frame over PCIe instead of 4 num_pdfs.
     e2e_topk = None
-    if args.e2e_topk > 0 and world == 1:
+    if not args.no_extra_legs and args.e2e_topk > 0 and world == 1:
         k = args.e2e_topk
         h_best = torch.empty((frames, 2 * k), dtype=torch.float32).pin_memory()
         model.set_output("topk", k=k)
@@ -359,9 +434,26 @@ def run_gpu(args):
         def step_topk():
             model.forward(h_pcm.numpy(), off, loglik=h_best.numpy(), argmax=h_am.numpy(), stream=stream)
         step_topk()
-        ms_topk = timed(step_topk, max(1, args.steps // 2))
-        e2e_topk = audio_per_step * max(1, args.steps // 2) / (ms_topk * 1e-3)
+        n_tk = max(1, min(3, args.steps))
+        ms_topk = timed(step_topk, n_tk)
+        e2e_topk = audio_per_step * n_tk / (ms_topk * 1e-3)
         model.set_output("dense")
+        del h_best
+
+    # The float paths of config 4 on the same batch (short legs: HBM-resident value only).  bf16x3 and
+    # fp32 (3xTF32) meet the 1e-3 log-likelihood bar; bf16 and tf32 single pass are fast modes outside it.
+    other = {}
+    if not args.no_extra_legs and world == 1 and args.precision == "int8":
+        for prec, in_tol in (("bf16x3", True), ("fp32", True), ("bf16", False), ("tf32", False)):
+            m2 = api.AcousticModelGpu(config=conf, precision=prec, device=local_rank)
+
+            def step2():
+                m2.forward(d_pcm, off, loglik=d_ll, argmax=d_am, stream=stream)
+            step2()
+            ms2 = timed(step2, 2)
+            other[prec] = {"value": round(audio_per_step * 2 / (ms2 * 1e-3), 1), "unit": UNIT,
+                           "ms_per_step": round(ms2 / 2, 3), "within_1e-3_of_reference_float": in_tol}
+            m2.close()
 
     if rank != 0:
         if world > 1:
@@ -375,38 +467,49 @@ def run_gpu(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     bf16_sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+    bf16_burst = peaks.get("bf16_tflops", 1590.0)
+    scale = {"int8": 2.0, "bf16": 1.0, "bf16x3": 1.0 / 3.0, "tf32": 0.5, "fp32": 0.5}[args.precision]
     if args.precision == "int8":
-        # no int8 figure was measured by the driver: the architectural ratio is 2x the bf16 rate
-        tensor_peak = 2.0 * bf16_sustained
-        peak_note = "2 x bf16_tflops_sustained (int8 tcgen05 rate is twice the bf16 rate; sustained, " \
-                    "because the kernel is timed inside a long step); %s" % peak_src
+        # no int8 figure was measured by the driver: the architectural ratio is 2x the bf16 rate.  The
+        # timed region is a fraction of a second at full clocks, so the BURST figure is the denominator.
+        tensor_peak = 2.0 * bf16_burst
+        peak_note = "2 x bf16_tflops (burst: the timed region runs at full clocks; int8 tcgen05 rate is twice " \
+                    "the bf16 rate); %s" % peak_src
     elif args.precision == "bf16":
-        tensor_peak = bf16_sustained
-        peak_note = "bf16_tflops_sustained; %s" % peak_src
+        tensor_peak = bf16_burst
+        peak_note = "bf16_tflops (burst); %s" % peak_src
     elif args.precision == "bf16x3":
-        tensor_peak = bf16_sustained / 3.0
-        peak_note = "bf16_tflops_sustained / 3 (three bf16 products per algorithmic multiply-add); %s" % peak_src
+        tensor_peak = bf16_burst / 3.0
+        peak_note = "bf16_tflops (burst) / 3 (three bf16 products per algorithmic multiply-add); %s" % peak_src
     else:
-        tensor_peak = 0.5 * bf16_sustained
-        peak_note = "0.5 x bf16_tflops_sustained (tf32 rate is half the bf16 rate%s); %s" % (
+        tensor_peak = 0.5 * bf16_burst
+        peak_note = "0.5 x bf16_tflops (burst; tf32 rate is half the bf16 rate%s); %s" % (
             "; the fp32 path spends 3 tf32 passes per product" if args.precision == "fp32" else "", peak_src)
     gemm_ms, gemm_n = prof["gemm"]
     fb_ms, fb_n = prof["fbank"]
     flops_step = frames * FLOPS_PER_FRAME          # this rank's share
-    traffic = None
+    traffic = hbm_step = pipe_ncu = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
-        per_row = json.load(open(tr_path)).get("gemm_%s_dram_bytes_per_row" % args.precision)
+        tr = json.load(open(tr_path))
+        per_row = tr.get("gemm_%s_dram_bytes_per_row" % args.precision)
         if per_row and gemm_n:
-            # ncu measured one hidden-layer launch; scale its bytes per activation row (1024 rows
-            # per 10 s utterance) to the rows one launch of this run's chunking covers
+            # ncu measured the launches of one 128-utterance chunk; the bytes per activation row (1024
+            # rows per 10 s utterance) of the average GEMM launch, times the rows one launch of this
+            # run's chunking covers
             launches_per_step = gemm_n / max(1, args.steps)
             traffic = int(per_row * n_utts * 1024 / max(1.0, launches_per_step / 7.0))
+        if args.precision == "int8" and tr.get("step_int8_dram_bytes_per_row"):
+            hbm_step = int(tr["step_int8_dram_bytes_per_row"] * n_utts * 1024)
+        pipe_ncu = tr.get("gemm_%s_tensor_pipe_active_pct" % args.precision)
     achieved = flops_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {
         "kernel": "gemm_kernel<%s> (tcgen05 cta_group::2, %d launches/step)" % (args.precision, gemm_n // max(1, args.steps)),
         "bound": "tensor", "achieved": round(achieved, 2), "peak": round(tensor_peak, 1), "unit": "TFLOP/s",
         "frac": round(achieved / tensor_peak, 4), "traffic": traffic,
+        "frac_burst": round(achieved / (scale * bf16_burst), 4),
+        "frac_sustained": round(achieved / (scale * bf16_sustained), 4),
+        "tensor_pipe_active_pct_ncu": pipe_ncu,
         "peak_source": peak_note,
         "algorithmic_flops_per_launch": round(flops_step * args.steps / max(1, gemm_n)),
         "avg_launch_ms": round(gemm_ms / max(1, gemm_n), 4),
@@ -434,6 +537,14 @@ def run_gpu(args):
         "roofline": roofline, "roofline_fbank": roofline_fbank,
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
     }
+    if hbm_step is not None:
+        out["hbm_bytes_per_step"] = {"value": hbm_step, "algorithmic": int(frames * (320 + 4 * model.num_pdfs)),
+                                     "source": "ncu dram__bytes_read+write of every launch of one 128-utterance "
+                                               "chunk (profiles/traffic.json), scaled by rows"}
+    if other:
+        out["float_paths"] = other
+    if base_more:
+        out["cpu_baselines_more"] = base_more
     if e2e_ll is not None:
         out["e2e_loglik"] = {"value": round(e2e_ll, 1), "unit": UNIT,
                              "d2h_bytes_per_step": int(frames * (4 + 4 * model.num_pdfs))}
@@ -664,8 +775,10 @@ def main():
     ap.add_argument("--precision", default="int8", choices=["int8", "bf16", "tf32", "fp32", "bf16x3"])
     ap.add_argument("--utts-per-gpu", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-loglik", action="store_true")
-    ap.add_argument("--e2e-topk", type=int, default=0,
+    ap.add_argument("--e2e-loglik", action="store_true", help="(kept for compatibility: now part of the default line)")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the short extra legs (e2e with dense / top-k rows to the host, float paths)")
+    ap.add_argument("--e2e-topk", type=int, default=64,
                     help="also time e2e with the k best (loglik, pdf) pairs per frame copied to the host")
     ap.add_argument("--workload", default="pipeline", choices=["pipeline", "frontend", "longform", "streaming"],
                     help="pipeline = the headline fbank+CMVN+AM step (default); frontend = config 2; "

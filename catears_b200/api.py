@@ -29,7 +29,7 @@ EXPORTS = [
     "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
     "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback", "ce_gpu_streams_create",
     "ce_gpu_streams_free", "ce_gpu_streams_open", "ce_gpu_streams_rows_ready", "ce_gpu_streams_process",
-    "ce_gpu_nnet_get_qparams",
+    "ce_gpu_nnet_get_qparams", "ce_gpu_nnet_chunks",
 ]
 ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
@@ -71,6 +71,7 @@ def lib():
     L.ce_gpu_rfft512.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     L.ce_gpu_nnet.argtypes = [vp, vp, i64p, C.c_int, vp, vp, vp]
     L.ce_gpu_forward.argtypes = [vp, vp, i64p, C.c_int, vp, vp, i64p, vp]
+    L.ce_gpu_nnet_chunks.argtypes = [vp, vp, i64p, C.c_int, vp, vp, vp]
     L.ce_gpu_nnet_keep_acc.argtypes = [vp, C.c_int]
     L.ce_gpu_model_set_output.argtypes = [vp, C.c_int, C.POINTER(C.c_int32), C.c_int]
     L.ce_gpu_model_output_width.argtypes = [vp]
@@ -363,6 +364,16 @@ class AcousticModelGpu:
         loglik, argmax = self._outputs(int(off[-1]), want_loglik, want_argmax, loglik, argmax)
         _check(lib().ce_gpu_nnet(self._h, _ptr(feats), p, off.size - 1, _ptr(loglik), _ptr(argmax),
                                  _stream(stream)), "ce_gpu_nnet")
+        return loglik, argmax
+
+    def nnet_chunks(self, feats, block_offsets, want_argmax=True, stream=None):
+        """ComputeBatch (src/am.cc:82-113) of many chunks: every block of rows carries its own context;
+        returns the packed rows of all blocks (block rows - left - right each)."""
+        off, p = _offsets(block_offsets)
+        n_out = int(np.maximum(np.diff(off) - self.left_context - self.right_context, 0).sum())
+        loglik, argmax = self._outputs(n_out, True, want_argmax, None, None)
+        _check(lib().ce_gpu_nnet_chunks(self._h, _ptr(feats), p, off.size - 1, _ptr(loglik), _ptr(argmax),
+                                        _stream(stream)), "ce_gpu_nnet_chunks")
         return loglik, argmax
 
     def forward(self, pcm, sample_offsets=None, want_loglik=True, want_argmax=True, loglik=None,

@@ -357,6 +357,27 @@ int ce_gpu_nnet(ce_gpu_model_t *m, const float *feats, const int64_t *utt_frame_
                      argmax, s);
 }
 
+int ce_gpu_nnet_chunks(ce_gpu_model_t *m, const float *feats, const int64_t *block_offsets, int n_blocks,
+                       float *loglik, int32_t *argmax, void *stream) {
+  if (!m) {
+    SetError("ce_gpu_nnet_chunks: null model");
+    return CE_GPU_EINVAL;
+  }
+  CE_CHECK(CheckOffsets(block_offsets, n_blocks, "ce_gpu_nnet_chunks"));
+  if (n_blocks == 0 || block_offsets[n_blocks] == block_offsets[0]) return CE_GPU_OK;
+  if (!feats) {
+    SetError("ce_gpu_nnet_chunks: null features");
+    return CE_GPU_EINVAL;
+  }
+  CE_CHECK(UseDevice(m->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t total = block_offsets[n_blocks];
+  const void *f_dev = nullptr;
+  CE_CHECK(StageIn(feats, sizeof(float) * (size_t)total * m->prog.feat_dim, &m->stage_feats, s, &f_dev));
+  return NnetForward(m, static_cast<const float *>(f_dev), block_offsets, n_blocks, false, loglik, argmax, s,
+                     /*contexted=*/true);
+}
+
 int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sample_offsets,
                    int n_utts, float *loglik, int32_t *argmax, int64_t *utt_frame_offsets_out,
                    void *stream) {

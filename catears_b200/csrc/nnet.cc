@@ -279,9 +279,12 @@ struct RowSpace {
   const UttRows *h_utts = nullptr;
 };
 
-int BuildRowSpace(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const int64_t *frame_off, int n_utts,
-                  cudaStream_t s, RowSpace *rs) {
-  const int L = m->left, R = m->right;
+// frame_off: input rows of every utterance; out_off: where its output rows go.  `contexted`: the input
+// rows of a block already carry their left / right context (ComputeBatch of a chunk, src/am.cc:82-113),
+// so nothing is replicated and a block of P rows yields P - L - R output rows.
+int BuildRowSpace(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const int64_t *frame_off, const int64_t *out_off,
+                  bool contexted, int n_utts, cudaStream_t s, RowSpace *rs) {
+  const int L = contexted ? 0 : m->left, R = contexted ? 0 : m->right;
   // ---- row space ----
   // Every utterance block starts at a multiple of kTileM rows (one utterance per GEMM tile).  When
   // the blocks are short -- micro-batches of live streams, a few frames plus context each -- that
@@ -324,7 +327,7 @@ int BuildRowSpace(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const int64_t *fram
     const int64_t T = frame_off[u + 1] - frame_off[u];
     hu[u].row_off = (int32_t)row_off64[u];
     hu[u].rows = T > 0 ? (int32_t)(T + L + R) : 0;
-    ho[u] = frame_off[u];
+    ho[u] = out_off[u];
     const int64_t end = (u + 1 < n_utts) ? row_off64[u + 1] : m_used;
     for (int64_t t = row_off64[u] / kRowGran; t < end / kRowGran; ++t) ht[t] = u;
   }
@@ -350,8 +353,8 @@ int BuildRowSpace(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const int64_t *fram
 // padding rows are copies, so the frames' min/max is the matrix's) for the first Quantize.
 int ChunkInput(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src, const float *feats_dev,
                const int64_t *frame_off, int n_utts, bool apply_cmvn, const RowSpace &rs, uint32_t *mm_first,
-               cudaStream_t s) {
-  const int L = m->left, R = m->right, F = m->prog.feat_dim;
+               cudaStream_t s, bool contexted) {
+  const int L = contexted ? 0 : m->left, R = contexted ? 0 : m->right, F = m->prog.feat_dim;
   std::vector<int64_t> local_off;
   const int64_t *feat_off = frame_off;
   if (src.pcm_dev) {
@@ -373,12 +376,13 @@ int ChunkInput(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src, 
 // model's precision -- for int8 that is Quantize(in) + MatMat_U8U8F32 + AddVec(b) per Linear layer,
 // the composition of SURVEY D3 -- everything else as the row-wise kernels of layers.cu.
 int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
-                        const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
-                        float *loglik_dev, int32_t *argmax_dev, cudaStream_t s) {
+                        const float *feats_dev, const int64_t *frame_off, const int64_t *out_off,
+                        bool contexted, int n_utts, bool apply_cmvn, float *loglik_dev, int32_t *argmax_dev,
+                        cudaStream_t s) {
   const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
   const int nb = (int)m->blocks.size();
   RowSpace rs;
-  CE_CHECK(BuildRowSpace(m, w, frame_off, n_utts, s, &rs));
+  CE_CHECK(BuildRowSpace(m, w, frame_off, out_off, contexted, n_utts, s, &rs));
   if (rs.M == 0) return CE_GPU_OK;
   const int M = rs.M;
   const int wmax = RoundUp(std::max(m->prog.max_dim, 4), 4);
@@ -400,7 +404,7 @@ int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSour
       if (m->n_pass == 3) CE_CHECK(w->act_lo[1].Reserve(sizeof(float) * (size_t)M * cmax));
     }
   }
-  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, nullptr, s));
+  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, nullptr, s, contexted));
 
   m->kept_valid = false;
   m->last_n_utts = n_utts;
@@ -532,15 +536,17 @@ int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSour
 // s: stream of the memory-bound kernels; s_gemm: stream of the GEMMs (== s when chunks are not
 // overlapped).
 int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src,
-                 const float *feats_dev, const int64_t *frame_off, int n_utts, bool apply_cmvn,
-                 float *loglik_dev, int32_t *argmax_dev, cudaStream_t s, cudaStream_t s_gemm) {
+                 const float *feats_dev, const int64_t *frame_off, const int64_t *out_off, bool contexted,
+                 int n_utts, bool apply_cmvn, float *loglik_dev, int32_t *argmax_dev, cudaStream_t s,
+                 cudaStream_t s_gemm) {
   const int L = m->left, R = m->right, F = m->prog.feat_dim, NP = m->prog.num_pdfs;
   const int nb = (int)m->blocks.size();
 
   if (m->prog.general)
-    return ForwardChunkGeneral(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, loglik_dev, argmax_dev, s);
+    return ForwardChunkGeneral(m, w, src, feats_dev, frame_off, out_off, contexted, n_utts, apply_cmvn, loglik_dev,
+                               argmax_dev, s);
   RowSpace rs;
-  CE_CHECK(BuildRowSpace(m, w, frame_off, n_utts, s, &rs));
+  CE_CHECK(BuildRowSpace(m, w, frame_off, out_off, contexted, n_utts, s, &rs));
   if (rs.M == 0) return CE_GPU_OK;
   const int M = rs.M;
   const bool gran = rs.gran;
@@ -574,7 +580,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   uint32_t *mm = w->minmax.as<uint32_t>();
   QParam *qp = w->qparams.as<QParam>();
   if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
-  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, m->kind == kKindI8 ? mm : nullptr, s));
+  CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, m->kind == kKindI8 ? mm : nullptr, s,
+                      contexted));
 
   // ---- network input in the operand format of the data path ----
   const int c0 = m->blocks[0].c_pad;
@@ -730,12 +737,23 @@ void CUDART_CB RowsReadyTrampoline(void *p) {
 }
 
 int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
-               int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
+               int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s,
+               bool contexted = false) {
   if (apply_cmvn && !m->has_cmvn) {
     SetError("the model was loaded without CMVN statistics");
     return CE_GPU_EINVAL;
   }
   const int L = m->left, R = m->right;
+  // output rows: one per input frame, or (contexted blocks) one per frame whose context is in the block
+  std::vector<int64_t> out_off_v;
+  const int64_t *out_off = frame_off;
+  if (contexted) {
+    out_off_v.assign(n_utts + 1, 0);
+    for (int u = 0; u < n_utts; ++u)
+      out_off_v[u + 1] = out_off_v[u] + std::max<int64_t>(0, frame_off[u + 1] - frame_off[u] - L - R);
+    out_off = out_off_v.data();
+  }
+  const int pad = contexted ? 0 : L + R;
   const int W = m->out_words();                          // 4-byte words per output row
   const bool ll_host = loglik && !IsDevicePtr(loglik);
   const bool am_host = argmax && !IsDevicePtr(argmax);
@@ -747,7 +765,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   }
   // The per-frame argmax is 4 bytes a frame: it is staged for the whole batch and copied out once,
   // so that no device-to-host copy sits between two chunks on the compute stream.
-  const int64_t total_frames = frame_off[n_utts] - frame_off[0];
+  const int64_t total_frames = out_off[n_utts] - out_off[0];
   if (am_host) CE_CHECK(m->stage_argmax_all.Reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(total_frames, 1)));
   bool used[2] = {false, false};
   bool ll_pending[2] = {false, false};
@@ -765,7 +783,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
                                       : m->max_chunk_rows;
     while (u1 < n_utts) {
       const int64_t T = frame_off[u1 + 1] - frame_off[u1];
-      const int64_t r = T > 0 ? (T + L + R + kTileM - 1) / kTileM * kTileM : 0;
+      const int64_t r = T > 0 ? (T + pad + kTileM - 1) / kTileM * kTileM : 0;
       if (u1 > u0 && rows + r > cap) break;
       rows += r;
       ++u1;
@@ -776,7 +794,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CUDA(cudaStreamWaitEvent(cs, m->inputs_ready, 0));
       used[chunk & 1] = true;
     }
-    const int64_t f0 = frame_off[u0], nf = frame_off[u1] - f0;
+    const int64_t f0 = out_off[u0], nf = out_off[u1] - f0;
     float *ll_dev = loglik;
     int32_t *am_dev = argmax;
     ce::DevBuf *ll_stage = &m->ws[chunk & 1].stage_loglik;   // two staging buffers, alternating
@@ -785,7 +803,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CHECK(ll_stage->Reserve(sizeof(float) * (size_t)nf * W));
       ll_dev = ll_stage->as<float>() - f0 * W;           // row f0 lands on the staging buffer's row 0
     }
-    if (am_host) am_dev = m->stage_argmax_all.as<int32_t>() - frame_off[0];   // whole batch, one copy at the end
+    if (am_host) am_dev = m->stage_argmax_all.as<int32_t>() - out_off[0];   // whole batch, one copy at the end
     PcmSource src = all;
     if (all.pcm_dev) src.sample_off = all.sample_off + u0;
     if (all.pcm_host && all.sample_off[u1] > all.sample_off[u0]) {
@@ -799,7 +817,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
       CE_CUDA(cudaEventRecord(m->copy_done[chunk], m->copy_stream));
       CE_CUDA(cudaStreamWaitEvent(cs, m->copy_done[chunk], 0));
     }
-    CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
+    CE_CHECK(ForwardChunk(m, w, src, feats_dev, frame_off + u0, out_off + u0, contexted, u1 - u0, apply_cmvn, ll_dev, am_dev, cs,
                           overlap ? w->stream_hi : cs));
     if ((ll_host || m->rows_cb) && nf > 0) {               // off the compute stream: the next chunk starts now
       CE_CUDA(cudaEventRecord(m->ll_ready[chunk & 1], cs));
@@ -809,7 +827,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
                                 cudaMemcpyDeviceToHost, m->d2h_stream));
       if (m->rows_cb) {                                    // the consumer may start on this chunk now
         if (am_host)
-          CE_CUDA(cudaMemcpyAsync(argmax + f0, m->stage_argmax_all.as<int32_t>() + (f0 - frame_off[0]),
+          CE_CUDA(cudaMemcpyAsync(argmax + f0, m->stage_argmax_all.as<int32_t>() + (f0 - out_off[0]),
                                   sizeof(int32_t) * (size_t)nf, cudaMemcpyDeviceToHost, m->d2h_stream));
         RowsReady *note = new RowsReady{m->rows_cb, m->rows_cb_user, u0, u1 - u0, f0, nf};
         cudaError_t e = cudaLaunchHostFunc(m->d2h_stream, RowsReadyTrampoline, note);
@@ -834,7 +852,7 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
   for (int i = 0; i < 2; ++i)
     if (ll_pending[i]) CE_CUDA(cudaStreamWaitEvent(s, m->ll_copied[i], 0));
   if (am_host && total_frames > 0 && !m->rows_cb) {      // (with a callback it went out chunk by chunk)
-    CE_CUDA(cudaMemcpyAsync(argmax + frame_off[0], m->stage_argmax_all.ptr, sizeof(int32_t) * (size_t)total_frames,
+    CE_CUDA(cudaMemcpyAsync(argmax + out_off[0], m->stage_argmax_all.ptr, sizeof(int32_t) * (size_t)total_frames,
                             cudaMemcpyDeviceToHost, s));
   }
   // host outputs are complete, and every callback has returned, on return
@@ -844,8 +862,8 @@ int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, co
 }  // namespace
 
 int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
-                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s) {
-  return ForwardAll(m, PcmSource(), feats_dev, frame_off, n_utts, apply_cmvn, loglik, argmax, s);
+                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s, bool contexted) {
+  return ForwardAll(m, PcmSource(), feats_dev, frame_off, n_utts, apply_cmvn, loglik, argmax, s, contexted);
 }
 
 int PcmForward(ce_gpu_model *m, const int16_t *pcm, int64_t total_samples,

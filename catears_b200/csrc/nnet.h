@@ -125,8 +125,11 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
 // stats while building the padded network input.  loglik [total_frames x m->out_words()] and
 // argmax [total_frames] may each be nullptr, a device pointer, or a host pointer (host outputs
 // are copied back chunk by chunk and are complete on return).
+// contexted: every block of rows already carries its own left / right context (one ComputeBatch of a
+// chunk, src/am.cc:82-113): nothing is replicated, a block of P rows yields P - L - R output rows, packed
+// block after block in loglik / argmax.
 int NnetForward(ce_gpu_model *m, const float *feats_dev, const int64_t *frame_off, int n_utts,
-                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s);
+                bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s, bool contexted = false);
 
 // The whole path from PCM: like NnetForward, but every chunk first runs the fbank kernel on its
 // own utterances (sample_off as in ce_gpu_fbank).  `pcm` is a device pointer or a host pointer;

@@ -334,16 +334,19 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
   const bool rows_host = rows && !IsDevicePtr(rows);
   float *rows_dev = rows;
   if (rows_total > 0) {
-    CE_CHECK(S->ll.Reserve(sizeof(float) * (size_t)xoff.back() * W));
+    CE_CHECK(S->ll.Reserve(sizeof(float) * (size_t)rows_total * W));
     if (rows_host) {
       CE_CHECK(S->rows_stage.Reserve(sizeof(float) * (size_t)rows_total * W));
       rows_dev = S->rows_stage.as<float>();
     }
   }
-  for (size_t k = 0; k < ready_idx.size(); ++k) {
-    const int i = ready_idx[k];
-    add(S->ll.as<float>() + (xoff[k] + L) * W, rows_dev + row_offsets[i] * W,
-        sizeof(float) * (size_t)plan[i].n_ready * W);
+  {                                                      // the forward pass packs block k's rows behind block k-1's
+    int64_t o = 0;
+    for (size_t k = 0; k < ready_idx.size(); ++k) {
+      const int i = ready_idx[k];
+      add(S->ll.as<float>() + o * W, rows_dev + row_offsets[i] * W, sizeof(float) * (size_t)plan[i].n_ready * W);
+      o += plan[i].n_ready;
+    }
   }
   for (int i = 0; i < n; ++i) {
     const Plan &p = plan[i];
@@ -374,7 +377,7 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
   CE_CHECK(run(g4, g5));
   if (rows_total > 0)
     CE_CHECK(NnetForward(m, S->x.as<float>(), xoff.data(), (int)ready_idx.size(), /*apply_cmvn=*/false,
-                         S->ll.as<float>(), nullptr, s));
+                         S->ll.as<float>(), nullptr, s, /*contexted=*/true));   // blocks carry their context
   CE_CHECK(run(g5, g6));
   if (rows_host && rows_total > 0)
     CE_CUDA(cudaMemcpyAsync(rows, rows_dev, sizeof(float) * (size_t)rows_total * W, cudaMemcpyDeviceToHost, s));

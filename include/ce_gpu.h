@@ -137,6 +137,16 @@ int ce_gpu_rfft512(const float *in, int n_frames, float *out, int device, void *
 int ce_gpu_nnet(ce_gpu_model_t *m, const float *feats, const int64_t *utt_frame_offsets,
                 int n_utts, float *loglik, int32_t *argmax, void *stream);
 
+/* AcousticModel::ComputeBatch (src/am.cc:82-113) for many chunks at once: block b = rows
+ * [block_offsets[b], block_offsets[b+1]) of `feats` is one chunk of frames that ALREADY carries its own
+ * context -- left_context rows in front of and right_context rows behind the frames it is evaluated
+ * for, the way AcousticModel::Process / EndOfStream stack their buffer (src/am.cc:115-164).  Nothing
+ * is replicated; a block of P rows yields P - left_context - right_context output rows (none if
+ * P <= left + right), packed block after block in `loglik` / `argmax`.  For int8 models each block is
+ * one Quantize matrix per layer, exactly like one ComputeBatch call of the reference. */
+int ce_gpu_nnet_chunks(ce_gpu_model_t *m, const float *feats, const int64_t *block_offsets, int n_blocks,
+                       float *loglik, int32_t *argmax, void *stream);
+
 /* The whole path: PCM -> fbank -> [CMVN if the model has stats] -> AM.
  * utt_frame_offsets_out (HOST, n_utts+1) may be NULL. */
 int ce_gpu_forward(ce_gpu_model_t *m, const int16_t *pcm, const int64_t *utt_sample_offsets,

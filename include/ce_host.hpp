@@ -314,17 +314,13 @@ class AcousticModel {
   }
 
   // batch_size output rows from the first batch_size + left + right buffered frames, which carry
-  // their own context (src/am.cc:82-113).  ce_gpu_nnet treats its input as a whole utterance and
-  // replicates the edges once more; the rows whose context is entirely real are [left, left + batch).
+  // their own context (src/am.cc:82-113): one block of ce_gpu_nnet_chunks.
   Status ComputeBatch(Instance *inst, int batch_size, Matrix *log_prob) const {
     const int in_rows = batch_size + left_context_ + right_context_;
     const int64_t foff[2] = {0, in_rows};
-    scratch_.Resize(in_rows, out_width_);
-    int rc = ce_gpu_nnet(model_, inst->feats_buffer.data(), foff, 1, scratch_.data.data(), nullptr, nullptr);
-    if (rc != CE_GPU_OK) return Status::FromGpu(rc);
     log_prob->Resize(batch_size, out_width_);
-    memcpy(log_prob->data.data(), scratch_.Row(left_context_), sizeof(float) * (size_t)batch_size * out_width_);
-    return Status::OK();
+    int rc = ce_gpu_nnet_chunks(model_, inst->feats_buffer.data(), foff, 1, log_prob->data.data(), nullptr, nullptr);
+    return rc != CE_GPU_OK ? Status::FromGpu(rc) : Status::OK();
   }
 
   Status SetOutput(int mode, const int32_t *ids, int n) {
@@ -459,14 +455,18 @@ class StreamBatch {
       ready.push_back(n_ready);
     }
     if (who.empty()) return Status::OK();
-    std::vector<float> ll((size_t)xoff.back() * P);
-    int rc = ce_gpu_nnet(am_->handle(), x.data(), xoff.data(), (int)who.size(), ll.data(), nullptr, nullptr);
+    int64_t n_rows = 0;
+    for (int r : ready) n_rows += r;
+    std::vector<float> ll((size_t)n_rows * P);
+    int rc = ce_gpu_nnet_chunks(am_->handle(), x.data(), xoff.data(), (int)who.size(), ll.data(), nullptr, nullptr);
     if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    int64_t o = 0;
     for (size_t k = 0; k < who.size(); ++k) {
       Stream *st = streams[who[k]];
       Matrix &out = (*rows)[who[k]];
       out.Resize(ready[k], P);
-      memcpy(out.data.data(), ll.data() + (size_t)(xoff[k] + L) * P, sizeof(float) * (size_t)ready[k] * P);
+      memcpy(out.data.data(), ll.data() + (size_t)o * P, sizeof(float) * (size_t)ready[k] * P);
+      o += ready[k];
       st->ctx.erase(st->ctx.begin(), st->ctx.begin() + (size_t)ready[k] * mel);
       st->rows_emitted += ready[k];
       if (st->ended) st->ctx.clear();

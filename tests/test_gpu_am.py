@@ -223,3 +223,36 @@ def test_two_handles_two_threads_concurrently(small_model, port):
     for tag in (0, 1):
         assert np.array_equal(results[tag][0], want_ll)
         assert np.array_equal(results[tag][1], want_am)
+
+
+def test_nnet_chunks_is_compute_batch_int8_bit_exact(ref, models, small_model):
+    """ce_gpu_nnet_chunks = AcousticModel::ComputeBatch (src/am.cc:82-113) of many chunks at once: every
+    block carries its own context the way Process / EndOfStream stack the buffer (chunk_size 16 here),
+    nothing is replicated, and for int8 every block is ONE Quantize matrix per layer -- the reference's
+    int8 composition run block by block (contexts 0: the block is taken as it is) gives the same rows."""
+    if ref is None:
+        pytest.skip("oracle/_ref was never built")
+    rng = np.random.default_rng(41)
+    T, L, R, chunk = 100, 13, 13, 16
+    x = (rng.standard_normal((T, 40)) * 2).astype(np.float32)
+    padded = np.concatenate([np.repeat(x[:1], L, 0), x, np.repeat(x[-1:], R, 0)])
+    blocks, a = [], 0
+    while a + chunk + L + R <= L + T:                      # Process: a batch once chunk + L + R frames are buffered
+        blocks.append(padded[a:a + chunk + L + R])
+        a += chunk
+    blocks.append(padded[a:])                              # EndOfStream: the rest with the right padding
+    off = np.concatenate([[0], np.cumsum([b.shape[0] for b in blocks])])
+    ll, am = models["int8"].nnet_chunks(np.concatenate(blocks), off)
+    assert ll.shape == (T, 96)
+    o = 0
+    for b in blocks:
+        want, _ = ref.u8_forward(small_model["nnet"], small_model["prior"], 0, 0, b)
+        n = b.shape[0] - L - R
+        assert want.shape == (n, 96)
+        assert np.abs(ll[o:o + n] - want).max() < 1e-5
+        check_argmax(am[o:o + n], want)
+        o += n
+    # float: the same rows as the whole utterance (chunked == whole, SURVEY 3.4)
+    whole, _ = models["fp32"].nnet(x)
+    ll32, _ = models["fp32"].nnet_chunks(np.concatenate(blocks), off)
+    assert np.abs(ll32 - whole).max() < 1e-4

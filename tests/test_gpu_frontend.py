@@ -94,6 +94,20 @@ def test_fbank_80_bins_vs_port(port):
     assert rel_err(got, want) < 1e-4
 
 
+@pytest.mark.parametrize("mel", [40, 80])
+def test_fbank_vs_independent_fp64_kaldi_formula(golden, mel):
+    """The pin for 80 mel bins (the reference aborts there, src/fbank.cc:155): tests/kaldi_fp64.py is an
+    independent float64 numpy statement of the Kaldi formula -- checked against the Kaldi golden dump
+    at 40 bins (tests/test_oracle.py) -- and the kernel must agree with it at 40 AND 80 bins to the same
+    1e-4 (relative to max(|ref|, 1)) it meets against the reference at 40."""
+    import kaldi_fp64
+    for pcm in (golden["hello_pcm"], golden["cat_pcm"], synth.synth_utterance(3, 32000)):
+        got = api.fbank(pcm, num_mel=mel)
+        want = kaldi_fp64.fbank(pcm, mel)
+        assert got.shape == want.shape
+        assert rel_err(got, want.astype(np.float32)) < 1e-4, mel
+
+
 def test_fbank_device_buffers_and_batch_equals_singles():
     import torch
     pcm, off = synth.synth_batch(5, 16000)

@@ -240,3 +240,25 @@ def test_am_streaming_equals_whole(ref, port, small_model, tmp_path):
     streamed = ref.am_forward(conf, x)
     assert streamed.shape == whole.shape
     assert np.abs(streamed - whole).max() < 2e-5
+
+
+def test_independent_fp64_fbank_pins_40_and_80_bins(golden, port):
+    """tests/kaldi_fp64.py (numpy float64, numpy's FFT, no code shared with the port) reproduces the
+    Kaldi golden dump at 40 bins to 1e-4 absolute, and the C restatement agrees with it at 40 and at
+    80 bins -- the size the reference cannot run (src/fbank.cc:155) and that no reference fixture
+    covers, so this independent statement of the one-parameter formula is its pin."""
+    import kaldi_fp64
+    from catears_b200 import synth
+    f40 = kaldi_fp64.fbank(golden["hello_pcm"], 40)
+    assert f40.shape == golden["kaldi_fbank"].shape
+    assert np.abs(f40 - golden["kaldi_fbank"]).max() < 1e-4
+    w = kaldi_fp64.mel_weights(40)
+    nz = (w > 0).sum(axis=1)
+    assert int(nz.sum()) == 492 and int(nz.max()) == 31          # SURVEY 8a row 8 [probe]
+    assert w[:, 0].sum() == 0 and w[:, 256].sum() == 0
+    for pcm in (golden["hello_pcm"], golden["cat_pcm"], synth.synth_utterance(3, 32000)):
+        for mel in (40, 80):
+            want = kaldi_fp64.fbank(pcm, mel)
+            got = port.fbank(pcm, mel=mel)
+            assert np.abs(got - want).max() / max(1.0, np.abs(want).max()) < 1e-4
+            assert (np.abs(got - want) / np.maximum(np.abs(want), 1.0)).max() < 1e-4, mel
