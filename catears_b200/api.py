@@ -29,7 +29,7 @@ EXPORTS = [
     "ce_gpu_partition", "ce_gpu_time_shards", "ce_gpu_model_set_output",
     "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback", "ce_gpu_streams_create",
     "ce_gpu_streams_free", "ce_gpu_streams_open", "ce_gpu_streams_rows_ready", "ce_gpu_streams_process",
-    "ce_gpu_nnet_get_qparams", "ce_gpu_nnet_chunks",
+    "ce_gpu_nnet_get_qparams", "ce_gpu_nnet_chunks", "ce_gpu_host_alloc", "ce_gpu_host_free",
 ]
 ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}

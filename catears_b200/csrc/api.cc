@@ -529,6 +529,26 @@ int ce_gpu_nnet_get_qparams(ce_gpu_model_t *m, int utt, float *scale, int32_t *z
   return nb;
 }
 
+// ---- pinned host memory for callers that do not link the CUDA runtime -------------------------
+
+void *ce_gpu_host_alloc(size_t bytes) {
+  if (DeviceCount() < 1) {
+    SetError("ce_gpu_host_alloc: no CUDA device");
+    return nullptr;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    SetError("cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+
+void ce_gpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 // ---- multi-GPU planning ---------------------------------------------------------------------
 
 int ce_gpu_partition(const int64_t *utt_frame_offsets, int n_utts, int n_parts, int32_t *part_begin) {

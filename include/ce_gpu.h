@@ -41,6 +41,7 @@
 #ifndef CE_GPU_H_
 #define CE_GPU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -264,6 +265,13 @@ int ce_gpu_gemm_u8(const uint8_t *a, float scale_a, int32_t zp_a, const uint8_t 
  * replacement for MatMat / cblas_sgemm, src/matrix.cc:300-323). */
 int ce_gpu_gemm_f32(const float *a, const float *b, int m, int n, int k, float *c,
                     int precision, int device, void *stream);
+
+/* ---- pinned host buffers --------------------------------------------------------------------
+ * Page-locked host memory (the row ring a CPU decoder reads, PCM staging): device <-> host copies
+ * to and from it run at the full PCIe rate and overlap compute.  For callers that do not link the
+ * CUDA runtime themselves (the ce_stt shim).  NULL (+ ce_gpu_last_error) on failure. */
+void *ce_gpu_host_alloc(size_t bytes);
+void ce_gpu_host_free(void *p);
 
 /* ---- multi-GPU planning (host only; utterances are independent, so there is no collective) ---- */
 

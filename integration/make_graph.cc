@@ -1,7 +1,11 @@
 // make_graph.cc -- TEST INFRASTRUCTURE: writes a small synthetic decoding graph for the drop-in
 // test of the unchanged reference decoder (the reference bundles no HCLG).
 //
-//   make_graph <dir> <num_pdfs> [n_words] [seed]
+//   make_graph <dir> <num_pdfs> [n_words] [seed] [first_word_label]
+//
+// first_word_label (default 1): the graph's words are labels first .. first + n_words - 1 of a symbol
+// table the caller supplies instead of the words.txt written here (the delta-LM test uses the
+// reference's test/data/lm.words.txt so that its G.pfst / lm.1order.bin fixtures apply).
 //
 // writes <dir>/HCLG.fst      fst::ConstFst<StdArc>: a word loop; every word is a left-to-right chain
 //                            of three emitting states with self-loops, input labels are
@@ -22,13 +26,14 @@
 
 int main(int argc, char **argv) {
   if (argc < 3) {
-    fprintf(stderr, "usage: %s <dir> <num_pdfs> [n_words] [seed]\n", argv[0]);
+    fprintf(stderr, "usage: %s <dir> <num_pdfs> [n_words] [seed] [first_word_label]\n", argv[0]);
     return 2;
   }
   const std::string dir = argv[1];
   const int num_pdfs = atoi(argv[2]);
   const int n_words = argc > 3 ? atoi(argv[3]) : 12;
   uint64_t rng = argc > 4 ? strtoull(argv[4], nullptr, 10) : 20261018ull;
+  const int first_label = argc > 5 ? atoi(argv[5]) : 1;
   auto next = [&rng]() {
     rng = rng * 6364136223846793005ull + 1442695040888963407ull;
     return (uint32_t)(rng >> 33);
@@ -48,7 +53,7 @@ int main(int argc, char **argv) {
   // in a state is expensive, so an utterance walks through many words
   const float word_cost = 0.1f, loop_cost = 1.5f;
   for (int w = 0; w < n_words; ++w) {
-    const int word_label = w + 1;
+    const int word_label = first_label + w;
     int prev = loop;
     for (int s = 0; s < 3; ++s) {
       const int st = g.AddState();

@@ -24,10 +24,12 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 BIN_REF = os.path.join(REF_DIR, "pocketkaldi_ref")
 BIN_GPU = os.path.join(REF_DIR, "pocketkaldi_gpu")
 MAKE_GRAPH = os.path.join(REF_DIR, "make_graph")
+STREAM_REF = os.path.join(REF_DIR, "stream_ref")
+STREAM_GPU = os.path.join(REF_DIR, "stream_gpu")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 pytestmark = pytest.mark.skipif(
-    not all(os.path.exists(p) for p in (BIN_REF, BIN_GPU, MAKE_GRAPH)),
+    not all(os.path.exists(p) for p in (BIN_REF, BIN_GPU, MAKE_GRAPH, STREAM_REF, STREAM_GPU)),
     reason="oracle/_ref drop-in binaries were never built (needs /root/reference: make -C oracle dropin)")
 
 
@@ -136,3 +138,89 @@ def test_unchanged_decoder_on_selected_gpu_rows(setup):
     assert approx.returncode == 0 and len(approx.stdout.split()) >= 20
     bad = run(BIN_GPU, setup["conf"], setup["wav"], env={"CE_STT_GPU_OUTPUT": "topk:0"})
     assert bad.returncode != 0
+
+
+def write_wav(path, pcm, width):
+    """Mono 16 kHz PCM with `width` bytes per sample (8-bit is written as the SIGNED bytes the
+    reference reads, src/pcm_reader.cc:36-40)."""
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(width)
+        w.setframerate(16000)
+        dt = {1: "<i1", 2: "<i2", 4: "<i4"}[width]
+        w.writeframes(np.asarray(pcm).astype(dt).tobytes())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("piece", [1024, 777, 100000])
+def test_streaming_partial_hypotheses_match_reference(setup, piece):
+    """src/main.cc:28-52 feeds ce_stt_process 1 KB at a time and the reference refreshes utt->hyp every 20
+    decoded frames (src/ce_stt.cc:326-327).  The GPU shim streams through ce_gpu_streams_* and hands the
+    decoder its rows in the reference's own batches (chunk_size 16 here), so after EVERY call utt->hyp
+    must be what the all-CPU reference holds: the drivers print it whenever it changes -- the two
+    transcripts (byte positions, partial texts, final text) must be identical.  Also an odd piece size
+    (samples split across calls, src/pcm_reader.cc:161,185-187) and one piece for the whole file."""
+    for audio in (setup["wav"], os.path.join(GOLDEN, "en-us-hello.wav")):
+        ref = subprocess.run([STREAM_REF, setup["conf"], audio, str(piece)], capture_output=True, text=True)
+        gpu = subprocess.run([STREAM_GPU, setup["conf"], audio, str(piece)], capture_output=True, text=True)
+        assert ref.returncode == 0, ref.stdout + ref.stderr
+        assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert gpu.stdout == ref.stdout, (audio, piece)
+        if audio == setup["wav"] and piece == 1024:
+            lines = ref.stdout.strip().splitlines()
+            assert sum(l.startswith("partial") for l in lines) >= 10      # the text really grows call by call
+            assert lines[-1].startswith("final")
+
+
+@pytest.mark.gpu
+def test_delta_lm_rescoring_is_wired(setup, tmp_path):
+    """large_lm / original_lm (src/ce_stt.cc:84-113): the unchanged DeltaLmFst rescoring on GPU rows gives
+    the reference's words.  The graph's words are entries of the reference's test/data/lm.words.txt so
+    that its G.pfst / lm.1order.bin fixtures (test/fst_test.cc:178-197) apply."""
+    import shutil
+    d = str(tmp_path)
+    m = input_sensitive_model(d)
+    subprocess.check_call([MAKE_GRAPH, d, "96", "12", "7", "3"], stdout=subprocess.DEVNULL)
+    os.replace(os.path.join(d, "tid2pdf.bin"), m["tid2pdf"])
+    for f in ("G.pfst", "lm.1order.bin", "lm.words.txt"):
+        shutil.copy(os.path.join(GOLDEN, f), d)
+    with open(m["conf"], "a") as f:
+        f.write("fst = HCLG.fst\nsymbol_table = lm.words.txt\nlarge_lm = G.pfst\noriginal_lm = lm.1order.bin\n")
+    ref = subprocess.run([STREAM_REF, m["conf"], setup["wav"]], capture_output=True, text=True)
+    gpu = subprocess.run([STREAM_GPU, m["conf"], setup["wav"]], capture_output=True, text=True)
+    assert ref.returncode == 0, ref.stdout + ref.stderr
+    assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+    assert gpu.stdout == ref.stdout
+    assert len(ref.stdout.strip().splitlines()[-1].split()) >= 10
+    # and it changes the result: without the delta LM the same graph decodes differently
+    plain = str(tmp_path / "plain.conf")
+    with open(m["conf"]) as f:
+        lines = [l for l in f if not l.startswith(("large_lm", "original_lm"))]
+    with open(plain, "w") as f:
+        f.writelines(lines)
+    base = subprocess.run([STREAM_REF, plain, setup["wav"]], capture_output=True, text=True)
+    assert base.returncode == 0 and base.stdout != ref.stdout
+
+
+@pytest.mark.gpu
+def test_pcm_widths(setup, tmp_path):
+    """src/pcm_reader.cc:168-182 passes 8-, 16- and 32-bit sample VALUES on unscaled.  8-bit and
+    16-bit-range 32-bit files decode to the reference's words; a 32-bit sample outside 16 bits is
+    refused with a message instead of being clamped."""
+    with wave.open(setup["wav"]) as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), np.int16)
+    # (8-bit: the signal divided by 64 and clipped; at 1/256 of the amplitude the REFERENCE's own decoder
+    # runs into its symbol-table assertion on this synthetic graph, so there is nothing to compare with)
+    cases = {"w32": (pcm.astype(np.int32), 4), "w8": (np.clip(pcm.astype(np.int32) // 64, -128, 127), 1)}
+    for name, (x, width) in cases.items():
+        path = str(tmp_path / (name + ".wav"))
+        write_wav(path, x, width)
+        ref = subprocess.run([STREAM_REF, setup["conf"], path], capture_output=True, text=True)
+        gpu = subprocess.run([STREAM_GPU, setup["conf"], path], capture_output=True, text=True)
+        assert ref.returncode == 0, ref.stdout + ref.stderr
+        assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert gpu.stdout == ref.stdout, name
+    loud = str(tmp_path / "loud32.wav")
+    write_wav(loud, pcm.astype(np.int32) * 4096, 4)
+    gpu = subprocess.run([STREAM_GPU, setup["conf"], loud], capture_output=True, text=True)
+    assert gpu.returncode != 0 and "does not fit 16 bits" in gpu.stderr
