@@ -15,6 +15,9 @@
 //   ce_host::AcousticModel::SelectPdfs / SelectTopK   narrower log_prob rows for the decoder
 //   ce_host::StreamBatch         many live utterances per call, per-stream state on the host
 //   ce_host::DeviceStreamBatch   the same with the state in device buffers (ce_gpu_streams_*)
+//   ce_host::ShardedModel        a list of utterances over ALL GPUs of the box: one model handle and
+//                                one host thread per GPU, rows handed to a pool of consumer threads
+//                                (CPU decoders) utterance by utterance while the GPUs keep working
 //
 // Differences, all deliberate: the types are plain (std::vector-backed Matrix instead of
 // pocketkaldi::Matrix<float>); every call that can fail on the device returns a Status instead of
@@ -29,8 +32,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ce_gpu.h"
@@ -541,6 +550,183 @@ class DeviceStreamBatch {
  private:
   const AcousticModel *am_;
   ce_gpu_streams_t *set_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// ShardedModel: the batch form over every GPU of the box (utterances are independent,
+// so there is no collective).  The utterance list is cut into contiguous, frame-balanced groups
+// (ce_gpu_partition), one per GPU; every GPU has its own model handle and its own host thread,
+// which runs ce_gpu_forward on its group chunk by chunk into a pinned host buffer; as soon as a
+// chunk's rows have arrived (ce_gpu_model_set_rows_callback) its utterances are queued for a pool
+// of consumer threads -- the CPU decoders -- so decoding of chunk c overlaps the GPU work on c + 1
+// and everything the other GPUs do.  Use a narrow row (SelectPdfs / SelectTopK): a dense row is
+// 4 num_pdfs bytes a frame of pinned memory and PCIe traffic.
+// ---------------------------------------------------------------------------------------------
+class ShardedModel {
+ public:
+  // One finished utterance: rows [n_frames x width] (valid during the call only), called once per
+  // utterance with >= 1 frame, from one of the consumer threads, in no particular order.
+  typedef std::function<void(int utt, const float *rows, int64_t n_frames, int width)> UtteranceFn;
+
+  ShardedModel() {}
+  ~ShardedModel() {
+    for (Shard &sh : shards_) {
+      ce_gpu_host_free(sh.rows);
+      ce_gpu_model_free(sh.model);
+    }
+  }
+  ShardedModel(const ShardedModel &) = delete;
+  ShardedModel &operator=(const ShardedModel &) = delete;
+
+  // One handle per device; `devices` empty = every visible device.
+  Status Read(const std::string &config_file, int precision = CE_GPU_PRECISION_FP32,
+              std::vector<int> devices = std::vector<int>()) {
+    if (devices.empty())
+      for (int d = 0; d < ce_gpu_device_count(); ++d) devices.push_back(d);
+    if (devices.empty()) return Status::RuntimeError("ShardedModel: no CUDA device");
+    for (int d : devices) {
+      Shard sh;
+      sh.device = d;
+      sh.model = ce_gpu_model_load_config(config_file.c_str(), precision, d);
+      if (!sh.model) return Status::FromGpu(CE_GPU_EIO);
+      shards_.push_back(sh);
+    }
+    return Status::FromGpu(ce_gpu_model_info(shards_[0].model, &num_pdfs_, &left_, &right_, nullptr, nullptr, nullptr));
+  }
+
+  Status SelectPdfs(const std::vector<int32_t> &pdf_ids) {
+    return SetOutput(CE_GPU_OUTPUT_SUBSET, pdf_ids.data(), (int)pdf_ids.size());
+  }
+  Status SelectTopK(int k) { return SetOutput(CE_GPU_OUTPUT_TOPK, nullptr, k); }
+  Status SelectAllPdfs() { return SetOutput(CE_GPU_OUTPUT_DENSE, nullptr, 0); }
+  int n_devices() const { return (int)shards_.size(); }
+  int num_pdfs() const { return num_pdfs_; }
+  int output_width() const { return shards_.empty() ? 0 : ce_gpu_model_output_width(shards_[0].model); }
+
+  // pcm: HOST samples of all utterances, utterance u = [sample_off[u], sample_off[u+1]).
+  // n_consumers threads call `fn`.  frame_off_out (nullable): frames of every utterance.
+  Status Forward(const int16_t *pcm, const int64_t *sample_off, int n_utts, const UtteranceFn &fn,
+                 int n_consumers = 1, std::vector<int64_t> *frame_off_out = nullptr) {
+    if (shards_.empty()) return Status::RuntimeError("ShardedModel::Forward before Read");
+    std::vector<int64_t> foff((size_t)n_utts + 1, 0);
+    const int64_t total = ce_gpu_frame_offsets(sample_off, n_utts, foff.data());
+    if (total < 0) return Status::FromGpu((int)total);
+    if (frame_off_out) *frame_off_out = foff;
+    const int n_parts = (int)shards_.size();
+    std::vector<int32_t> part((size_t)n_parts + 1, 0);
+    int rc = ce_gpu_partition(foff.data(), n_utts, n_parts, part.data());
+    if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+
+    Queue q;
+    std::vector<Status> status((size_t)n_parts);
+    std::vector<std::thread> gpus, consumers;
+    for (int c = 0; c < std::max(1, n_consumers); ++c)
+      consumers.emplace_back([&]() {
+        Item it;
+        while (q.Pop(&it)) fn(it.utt, it.rows, it.n_frames, it.width);
+      });
+    for (int p = 0; p < n_parts; ++p)
+      gpus.emplace_back([&, p]() { status[p] = RunShard(&shards_[p], pcm, sample_off, foff.data(), part[p], part[p + 1], &q); });
+    for (std::thread &t : gpus) t.join();
+    q.Close();
+    for (std::thread &t : consumers) t.join();
+    for (const Status &st : status)
+      if (!st.ok()) return st;
+    return Status::OK();
+  }
+
+ private:
+  struct Shard {
+    int device = 0;
+    ce_gpu_model_t *model = nullptr;
+    float *rows = nullptr;              // pinned host rows of the group being evaluated
+    size_t rows_bytes = 0;
+  };
+  struct Item {
+    int utt;
+    const float *rows;
+    int64_t n_frames;
+    int width;
+  };
+  class Queue {
+   public:
+    void Push(const Item &it) {
+      std::lock_guard<std::mutex> lock(mu_);
+      items_.push_back(it);
+      cv_.notify_one();
+    }
+    void Close() {
+      std::lock_guard<std::mutex> lock(mu_);
+      closed_ = true;
+      cv_.notify_all();
+    }
+    bool Pop(Item *it) {
+      std::unique_lock<std::mutex> lock(mu_);
+      cv_.wait(lock, [&]() { return closed_ || !items_.empty(); });
+      if (items_.empty()) return false;
+      *it = items_.front();
+      items_.pop_front();
+      return true;
+    }
+
+   private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Item> items_;
+    bool closed_ = false;
+  };
+  struct ChunkCtx {                     // what the rows-ready callback of one Forward call needs
+    Queue *q;
+    const int64_t *foff;                // frame offsets of ALL utterances
+    int first_utt;                      // of this shard's group
+    int64_t first_frame;
+    const float *rows;
+    int width;
+  };
+  static void RowsReady(void *user, int first_utt, int n_utts, int64_t, int64_t) {
+    const ChunkCtx *c = static_cast<const ChunkCtx *>(user);
+    for (int u = first_utt; u < first_utt + n_utts; ++u) {          // indices within the group
+      const int g = c->first_utt + u;
+      const int64_t n = c->foff[g + 1] - c->foff[g];
+      if (n > 0) c->q->Push(Item{g, c->rows + (size_t)(c->foff[g] - c->first_frame) * c->width, n, c->width});
+    }
+  }
+
+  Status RunShard(Shard *sh, const int16_t *pcm, const int64_t *sample_off, const int64_t *foff, int u0, int u1,
+                  Queue *q) {
+    if (u1 <= u0) return Status::OK();
+    const int width = ce_gpu_model_output_width(sh->model);
+    const int64_t frames = foff[u1] - foff[u0];
+    if (frames == 0) return Status::OK();
+    const size_t bytes = sizeof(float) * (size_t)frames * width;
+    if (bytes > sh->rows_bytes) {
+      ce_gpu_host_free(sh->rows);
+      sh->rows = static_cast<float *>(ce_gpu_host_alloc(bytes));
+      sh->rows_bytes = sh->rows ? bytes : 0;
+      if (!sh->rows) return Status::FromGpu(CE_GPU_ENOMEM);
+    }
+    // the group's own offset arrays start at 0 (the sample data is addressed from its first sample)
+    std::vector<int64_t> soff((size_t)(u1 - u0) + 1);
+    for (int u = u0; u <= u1; ++u) soff[u - u0] = sample_off[u] - sample_off[u0];
+    ChunkCtx ctx = {q, foff, u0, foff[u0], sh->rows, width};
+    int rc = ce_gpu_model_set_rows_callback(sh->model, &ShardedModel::RowsReady, &ctx);
+    if (rc == CE_GPU_OK)
+      rc = ce_gpu_forward(sh->model, pcm + sample_off[u0], soff.data(), u1 - u0, sh->rows, nullptr, nullptr, nullptr);
+    Status st = Status::FromGpu(rc);                     // (before the next call overwrites the message)
+    ce_gpu_model_set_rows_callback(sh->model, nullptr, nullptr);
+    return st;
+  }
+
+  Status SetOutput(int mode, const int32_t *ids, int n) {
+    for (Shard &sh : shards_) {
+      int rc = ce_gpu_model_set_output(sh.model, mode, ids, n);
+      if (rc != CE_GPU_OK) return Status::FromGpu(rc);
+    }
+    return Status::OK();
+  }
+
+  std::vector<Shard> shards_;
+  int num_pdfs_ = 0, left_ = 0, right_ = 0;
 };
 
 }  // namespace ce_host

@@ -26,6 +26,7 @@ BIN_GPU = os.path.join(REF_DIR, "pocketkaldi_gpu")
 MAKE_GRAPH = os.path.join(REF_DIR, "make_graph")
 STREAM_REF = os.path.join(REF_DIR, "stream_ref")
 STREAM_GPU = os.path.join(REF_DIR, "stream_gpu")
+BIN_BATCH = os.path.join(REF_DIR, "pocketkaldi_batch")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 pytestmark = pytest.mark.skipif(
@@ -224,3 +225,35 @@ def test_pcm_widths(setup, tmp_path):
     write_wav(loud, pcm.astype(np.int32) * 4096, 4)
     gpu = subprocess.run([STREAM_GPU, setup["conf"], loud], capture_output=True, text=True)
     assert gpu.returncode != 0 and "does not fit 16 bits" in gpu.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BIN_BATCH), reason="oracle/_ref/pocketkaldi_batch was never built")
+def test_batch_decode_over_all_gpus_matches_reference_scp(setup, tmp_path):
+    """SURVEY 8e through the C++ surface: `pocketkaldi_batch <conf> <scp>` evaluates the whole list as one
+    batch over every visible GPU (ce_host::ShardedModel: ce_gpu_partition, one handle + host thread per
+    GPU, graph-reachable pdf columns into pinned host rows) and decodes every utterance with the
+    reference's unchanged Decoder on a CPU thread pool as its rows arrive.  The "<name> <words>" lines
+    must equal the all-CPU reference's scp mode (src/main.cc:55-84), utterance for utterance."""
+    rng = np.random.default_rng(12)
+    lines = []
+    for i in range(14):                                   # ragged lengths, one shorter than a frame
+        n = [160000, 48000, 8000, 200, 100000][i % 5]
+        t = np.arange(n) / 16000.0
+        f = 300 + 2500 * (0.5 + 0.5 * np.sin(2 * np.pi * (0.3 + 0.1 * i) * t))
+        x = 5000 * np.sin(2 * np.pi * np.cumsum(f) / 16000.0) * (0.3 + 0.7 * (np.sin(2 * np.pi * 2.5 * t) > 0))
+        x = x + 60 * rng.standard_normal(n)
+        path = str(tmp_path / ("u%02d.wav" % i))
+        write_wav(path, np.clip(np.round(x), -32768, 32767), 2)
+        lines.append("utt%02d %s\n" % (i, path))
+    lines.append("hello %s\n" % os.path.join(GOLDEN, "en-us-hello.wav"))
+    scp = str(tmp_path / "many.scp")
+    with open(scp, "w") as f:
+        f.writelines(lines)
+    ref = run(BIN_REF, setup["conf"], scp)
+    assert ref.returncode == 0, ref.stdout + ref.stderr
+    for threads in ("1", "6"):
+        gpu = subprocess.run([BIN_BATCH, setup["conf"], scp, threads], capture_output=True, text=True)
+        assert gpu.returncode == 0, gpu.stdout + gpu.stderr
+        assert gpu.stdout == ref.stdout, threads
+    assert len(ref.stdout.strip().splitlines()) == 15
