@@ -775,7 +775,7 @@ def run_streaming(args):
     n, per_call = args.streams, 16 * args.stream_ms
     streams = api.StreamSet(model, n)
     slots = [streams.open() for _ in range(n)]
-    audio = synth.synth_utterance(11, per_call * (args.steps + args.warmup + 1), seed=11)
+    audio = synth.synth_utterance(11, per_call * (2 * args.steps + args.warmup + 1), seed=11)
     eos = [False] * n
 
     def step(c):
@@ -783,12 +783,17 @@ def run_streaming(args):
         return streams.process(slots, [piece] * n, eos)
     for c in range(args.warmup):
         step(c)
-    api.profile_enable(True)
     wall = []
+    streams.call_stats(reset=True)
     for c in range(args.warmup, args.warmup + args.steps):
         t0 = time.perf_counter()
         rows = step(c)
         wall.append(1e3 * (time.perf_counter() - t0))
+    n_calls, enq_us, tot_us = streams.call_stats()
+    # kernel time per call: the same calls once more with CUDA events around every launch
+    api.profile_enable(True)
+    for c in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
+        step(c)
     prof = api.profile_read()
     api.profile_enable(False)
     ms = float(np.median(wall))
@@ -799,6 +804,11 @@ def run_streaming(args):
         "dtype": DTYPES[args.precision],
         "data": "synthetic",
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+        "abi_ms_per_call": {"total": round(tot_us / max(1, n_calls) * 1e-3, 3),
+                            "until_all_work_is_queued": round(enq_us / max(1, n_calls) * 1e-3, 3),
+                            "kernels": round(sum(v[0] for v in prof.values()) / args.steps, 3),
+                            "note": "inside ce_gpu_streams_process (C ABI); ms_per_step is the Python caller's wall "
+                                    "time (ctypes marshalling of the per-slot arrays included)"},
         "config": {"workload": "streaming: %d live streams x %d ms of new audio per call "
                                "(ce_gpu_streams_process, state on the device), fbank + CMVN + TDNN, %s GEMMs, "
                                "rows = 64 best (loglik, pdf) pairs per frame to the host; median wall time per call"

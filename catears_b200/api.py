@@ -30,6 +30,7 @@ EXPORTS = [
     "ce_gpu_model_output_width", "ce_gpu_model_set_rows_callback", "ce_gpu_streams_create",
     "ce_gpu_streams_free", "ce_gpu_streams_open", "ce_gpu_streams_rows_ready", "ce_gpu_streams_process",
     "ce_gpu_nnet_get_qparams", "ce_gpu_nnet_chunks", "ce_gpu_host_alloc", "ce_gpu_host_free",
+    "ce_gpu_streams_call_stats",
 ]
 ROWS_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64)
 OUTPUT_MODES = {"dense": 0, "subset": 1, "topk": 2}
@@ -85,6 +86,7 @@ def lib():
     L.ce_gpu_streams_rows_ready.argtypes = [vp, ip, C.c_int, ip, C.POINTER(C.c_ubyte)]
     L.ce_gpu_streams_process.argtypes = [vp, ip, C.c_int, C.POINTER(vp), ip, C.POINTER(C.c_ubyte), vp,
                                          C.c_int64, i64p, vp]
+    L.ce_gpu_streams_call_stats.argtypes = [vp, i64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
     L.ce_gpu_nnet_get_acc.argtypes = [vp, C.c_int, vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ce_gpu_nnet_get_qparams.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int]
     L.ce_gpu_quantize.argtypes = [vp, C.c_int64, C.c_int, vp, C.POINTER(C.c_float),
@@ -425,6 +427,13 @@ class StreamSet:
             self._h = None
 
     __del__ = close
+
+    def call_stats(self, reset=False):
+        """(calls, enqueue_us, total_us) spent inside ce_gpu_streams_process so far."""
+        n, a, b = C.c_int64(), C.c_double(), C.c_double()
+        _check(lib().ce_gpu_streams_call_stats(self._h, C.byref(n), C.byref(a), C.byref(b), 1 if reset else 0),
+               "ce_gpu_streams_call_stats")
+        return n.value, a.value, b.value
 
     def open(self):
         slot = lib().ce_gpu_streams_open(self._h)

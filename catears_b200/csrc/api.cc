@@ -6,6 +6,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <exception>
 #include <map>
 #include <memory>
 #include <string>
@@ -95,9 +96,27 @@ int ce_gpu_profile_trace(int cap, int32_t *cat, double *t0_ms, double *t1_ms) {
 
 // ---- model ----------------------------------------------------------------------------
 
+namespace {
+ce_gpu_model_t *ModelLoad(const char *nnet_path, const char *prior_path, const char *cmvn_stats_path,
+                          int left_context, int right_context, int precision, int device);
+}  // namespace
+
+// No C++ exception may cross the C ABI: an allocation failure while reading or packing a model
+// (std::bad_alloc, std::length_error) becomes NULL + a message like every other load error.
 ce_gpu_model_t *ce_gpu_model_load(const char *nnet_path, const char *prior_path,
                                   const char *cmvn_stats_path, int left_context,
                                   int right_context, int precision, int device) {
+  try {
+    return ModelLoad(nnet_path, prior_path, cmvn_stats_path, left_context, right_context, precision, device);
+  } catch (const std::exception &e) {
+    SetError("ce_gpu_model_load: %s", e.what());
+    return nullptr;
+  }
+}
+
+namespace {
+ce_gpu_model_t *ModelLoad(const char *nnet_path, const char *prior_path, const char *cmvn_stats_path,
+                          int left_context, int right_context, int precision, int device) {
   if (!nnet_path || !prior_path || left_context < 0 || right_context < 0) {
     SetError("ce_gpu_model_load: bad arguments");
     return nullptr;
@@ -119,6 +138,7 @@ ce_gpu_model_t *ce_gpu_model_load(const char *nnet_path, const char *prior_path,
     return nullptr;
   return m.release();
 }
+}  // namespace
 
 ce_gpu_model_t *ce_gpu_model_load_config(const char *config_path, int precision, int device) {
   if (!config_path) {

@@ -261,10 +261,12 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
                int pad_left, int pad_right, float *out_dev, int64_t out_stride, Table *utts,
                cudaStream_t s, const CmvnResume *resume, uint32_t *minmax_dev) {
   if (n_utts <= 0) return CE_GPU_OK;
+  HostMark(nullptr);
   const CmvnStep *steps = nullptr;
   if (global_stats_dev) CE_CHECK(GetSteps(global_count, &steps));
   size_t bytes = sizeof(CmvnUtt) * (size_t)n_utts;
   CE_CHECK(utts->Acquire(bytes));
+  HostMark("cmvn: acquire");
   CmvnUtt *h = utts->host<CmvnUtt>();
   for (int u = 0; u < n_utts; ++u) {
     h[u].in_row = frame_off[u];
@@ -277,7 +279,9 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
       h[u].t_base = (int32_t)std::min<int64_t>(resume->t_base[u], 0x7fffffff);
     }
   }
+  HostMark("cmvn: table");
   CE_CHECK(utts->Upload(bytes, s));
+  HostMark("cmvn: upload");
   if (num_mel > kMaxMel) {
     SetError("CmvnLaunch: num_mel %d > %d", num_mel, kMaxMel);
     return CE_GPU_EINVAL;
@@ -300,6 +304,7 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
                                                            tile_frames, pad_left, pad_right, out_dev,
                                                            out_stride, resume ? resume->state_dev : nullptr, minmax_dev);
   CE_LAUNCHED();
+  HostMark("cmvn: launch");
   return CE_GPU_OK;
 }
 

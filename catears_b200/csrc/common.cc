@@ -1,6 +1,16 @@
 // common.cc -- error state, device selection and workspace buffers of libce_gpu.so.
 #include "common.h"
 
+#include <algorithm>
+
+#include <string>
+
+#include <mutex>
+
+#include <map>
+
+#include <chrono>
+
 #include <string.h>
 
 namespace ce {
@@ -248,4 +258,33 @@ int StageOut(void *dst, const void *dev_src, size_t bytes, cudaStream_t s) {
   return CE_GPU_OK;
 }
 
+}  // namespace ce
+
+namespace ce {
+namespace {
+struct HostProfState {
+  std::map<std::string, std::pair<double, long>> acc;
+  std::mutex mu;
+  ~HostProfState() {
+    for (auto &kv : acc)
+      fprintf(stderr, "host-prof %-28s %10.1f us total %8ld calls %8.2f us/call\n", kv.first.c_str(), kv.second.first,
+              kv.second.second, kv.second.first / std::max<long>(1, kv.second.second));
+  }
+};
+HostProfState g_host_prof;
+}  // namespace
+
+void HostMark(const char *label) {
+  static const bool on = getenv("CE_GPU_HOST_PROF") != nullptr;
+  if (!on) return;
+  static thread_local double last = 0;
+  const double t = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (label && last > 0) {
+    std::lock_guard<std::mutex> lock(g_host_prof.mu);
+    auto &e = g_host_prof.acc[label];
+    e.first += t - last;
+    e.second += 1;
+  }
+  last = t;
+}
 }  // namespace ce

@@ -65,6 +65,10 @@ int ProfRead(double *ms, int64_t *launches);
 // number of records written (<= cap) or a negative error, and clears the records.
 int ProfTrace(int cap, int32_t *cat, double *t0_ms, double *t1_ms);
 
+// -- host-time probe (CE_GPU_HOST_PROF=1): HostMark("label") adds the host time since the previous mark
+// of this thread to the label's total; totals are printed at process exit.  A debugging aid.
+void HostMark(const char *label);
+
 // -- device selection -----------------------------------------------------------
 // Makes `device` current; fails with CE_GPU_ENODEVICE when there is none / not sm_100.
 int UseDevice(int device);

@@ -757,8 +757,45 @@ int GetEncodeFn(EncodeTiledFn *out) {
   return CE_GPU_OK;
 }
 
+// cuTensorMapEncodeTiled costs microseconds of host time, and a streaming micro-batch call makes 42 of them
+// for a millisecond of kernels -- with the same operands call after call.  Encoded maps are therefore
+// kept per host thread, keyed by everything that goes into them.
+struct MapKey {
+  const void *base;
+  int64_t rows, cols, ld;
+  int box_rows, tag;                                     // tag: operand kind, or 16 + bf16 for output maps
+  bool operator==(const MapKey &o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && tag == o.tag;
+  }
+};
+struct MapCache {
+  static constexpr int kEntries = 128;
+  MapKey key[kEntries];
+  CUtensorMap map[kEntries];
+  int n = 0, next = 0;
+  bool Find(const MapKey &k, CUtensorMap *out) const {
+    for (int i = 0; i < n; ++i)
+      if (key[i] == k) {
+        *out = map[i];
+        return true;
+      }
+    return false;
+  }
+  void Put(const MapKey &k, const CUtensorMap &m) {
+    const int i = n < kEntries ? n++ : (next++ % kEntries);
+    key[i] = k;
+    map[i] = m;
+  }
+};
+MapCache &Maps() {
+  static thread_local MapCache c;
+  return c;
+}
+
 // 2-D map over a row-major [rows x cols] matrix, box = [box_rows x 128 bytes], 128B swizzle.
 int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows, CUtensorMap *map) {
+  const MapKey mk = {base, rows, cols, cols, box_rows, kind};
+  if (Maps().Find(mk, map)) return CE_GPU_OK;
   EncodeTiledFn fn;
   CE_CHECK(GetEncodeFn(&fn));
   const int elt = KindEltBytes(kind);
@@ -782,12 +819,15 @@ int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows
              (long long)rows, (long long)cols, kind);
     return CE_GPU_ECUDA;
   }
+  Maps().Put(mk, *map);
   return CE_GPU_OK;
 }
 
 // 2-D map for the TMA stores of the epilogue: [rows x cols] window of a row-major matrix with row
 // stride ld (elements), box = 32 rows x 128 bytes, 128B swizzle.
 int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap *map) {
+  const MapKey mk = {base, rows, cols, ld, 32, 16 + (bf16 ? 1 : 0)};
+  if (Maps().Find(mk, map)) return CE_GPU_OK;
   EncodeTiledFn fn;
   CE_CHECK(GetEncodeFn(&fn));
   const int elt = bf16 ? 2 : 4;
@@ -809,6 +849,7 @@ int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t 
              (int)r, (long long)rows, (long long)cols, (long long)ld);
     return CE_GPU_ECUDA;
   }
+  Maps().Put(mk, *map);
   return CE_GPU_OK;
 }
 

@@ -29,7 +29,18 @@ class File {
       SetError("unable to open %s", path.c_str());
       return CE_GPU_EIO;
     }
+    if (fseek(f_, 0, SEEK_END) == 0) {
+      size_ = ftell(f_);
+      fseek(f_, 0, SEEK_SET);
+    }
     return CE_GPU_OK;
+  }
+  // true if `bytes` more bytes can still be read (dimensions in a corrupt header must not drive an
+  // allocation the file cannot back)
+  bool Has(uint64_t bytes) const {
+    if (size_ < 0) return true;
+    const long pos = ftell(f_);
+    return pos >= 0 && bytes <= (uint64_t)(size_ - pos);
   }
   int Read(void *dst, size_t n) {
     if (n && fread(dst, 1, n, f_) != n) {
@@ -52,6 +63,7 @@ class File {
 
  private:
   FILE *f_ = nullptr;
+  long size_ = -1;
   std::string path_;
 };
 
@@ -60,7 +72,7 @@ int ReadVec(File *f, std::vector<float> *v) {
   int32_t bytes = 0, dim = 0;
   CE_CHECK(f->I32(&bytes));
   CE_CHECK(f->I32(&dim));
-  if (dim < 0 || bytes != 4 * dim + 4) {
+  if (dim < 0 || bytes != 4 * dim + 4 || !f->Has(4ull * (uint64_t)dim)) {
     SetError("%s: VEC0 section size mismatch (%d bytes for dim %d)", f->path().c_str(), bytes, dim);
     return CE_GPU_EIO;
   }
@@ -74,7 +86,7 @@ int ReadMat(File *f, std::vector<float> *m, int *rows, int *cols) {
   CE_CHECK(f->I32(&sz));
   CE_CHECK(f->I32(&r));
   CE_CHECK(f->I32(&c));
-  if (sz != 8 || r < 0 || c < 0) {
+  if (sz != 8 || r < 0 || c < 0 || !f->Has((uint64_t)r * (12ull + 4ull * (uint64_t)c))) {
     SetError("%s: MAT0 header corrupt (size %d, %d x %d)", f->path().c_str(), sz, r, c);
     return CE_GPU_EIO;
   }
@@ -190,6 +202,11 @@ int ReadConfigFile(const std::string &path, std::map<std::string, std::string> *
   char buf[4096];
   int rc = CE_GPU_OK;
   while (fgets(buf, sizeof(buf), f)) {
+    if (strlen(buf) == sizeof(buf) - 1 && buf[sizeof(buf) - 2] != '\n') {
+      SetError("%s: line longer than %zu bytes", path.c_str(), sizeof(buf) - 2);
+      rc = CE_GPU_EIO;
+      break;
+    }
     std::string line = Trim(buf);
     if (line.empty() || line[0] == '#') continue;
     size_t eq = line.find('=');

@@ -545,8 +545,10 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   if (m->prog.general)
     return ForwardChunkGeneral(m, w, src, feats_dev, frame_off, out_off, contexted, n_utts, apply_cmvn, loglik_dev,
                                argmax_dev, s);
+  HostMark(nullptr);
   RowSpace rs;
   CE_CHECK(BuildRowSpace(m, w, frame_off, out_off, contexted, n_utts, s, &rs));
+  HostMark("chunk: row space");
   if (rs.M == 0) return CE_GPU_OK;
   const int M = rs.M;
   const bool gran = rs.gran;
@@ -579,10 +581,13 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   // ---- fbank (when the input is PCM), replicate padding (+ CMVN) into x0, first min/max ----
   uint32_t *mm = w->minmax.as<uint32_t>();
   QParam *qp = w->qparams.as<QParam>();
+  HostMark("chunk: reserve");
   if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
+  HostMark("chunk: init minmax");
   CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, m->kind == kKindI8 ? mm : nullptr, s,
                       contexted));
 
+  HostMark("chunk: workspace + input");
   // ---- network input in the operand format of the data path ----
   const int c0 = m->blocks[0].c_pad;
   if (m->kind == kKindI8) {
@@ -601,6 +606,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
 
   m->kept_valid = false;
   m->last_n_utts = n_utts;
+  HostMark("chunk: first quantize");
   for (int b = 0; b < nb; ++b) {
     const DeviceBlock &D = m->blocks[b];
     const bool last = (b == nb - 1);
@@ -699,7 +705,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
       CE_CUDA(cudaEventRecord(w->to_hi, s));
       CE_CUDA(cudaStreamWaitEvent(s_gemm, w->to_hi, 0));
     }
+    HostMark("chunk: gemm args");
     CE_CHECK(GemmLaunch(m->kind, ops, a, s_gemm));
+    HostMark("chunk: GemmLaunch");
     if (s_gemm != s && (m->kind == kKindI8 || last)) {   // float paths chain GEMM -> GEMM
       CE_CUDA(cudaEventRecord(w->to_lo, s_gemm));
       CE_CUDA(cudaStreamWaitEvent(s, w->to_lo, 0));
@@ -713,10 +721,12 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     }
   }
 
+  HostMark("chunk: quantize launches");
   CE_CHECK(FinalizeLaunch(w->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
                           w->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
                           m->log_prior.as<float>(), loglik_dev, m->out_words(), argmax_dev, s,
                           m->out_sel));
+  HostMark("chunk: finalize");
   return CE_GPU_OK;
 }
 
@@ -736,9 +746,33 @@ void CUDART_CB RowsReadyTrampoline(void *p) {
   delete r;
 }
 
+int ForwardAllImpl(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
+                   int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s, bool contexted);
+
+// A call that fails half way (e.g. the workspace cannot grow for a later chunk) may already have queued
+// copies into the caller's host buffers and rows-ready callbacks for earlier chunks: nothing of that
+// may still be in flight when the error is returned, or the caller would free buffers under it.
 int ForwardAll(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
                int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s,
                bool contexted = false) {
+  const int rc = ForwardAllImpl(m, all, feats_dev, frame_off, n_utts, apply_cmvn, loglik, argmax, s, contexted);
+  if (rc != CE_GPU_OK) {
+    const std::string msg = LastError();                 // keep the first error's message
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(m->copy_stream);
+    cudaStreamSynchronize(m->d2h_stream);
+    for (int i = 0; i < 2; ++i) {
+      if (m->ws[i].stream) cudaStreamSynchronize(m->ws[i].stream);
+      if (m->ws[i].stream_hi) cudaStreamSynchronize(m->ws[i].stream_hi);
+    }
+    cudaGetLastError();
+    SetError("%s", msg.c_str());
+  }
+  return rc;
+}
+
+int ForwardAllImpl(ce_gpu_model *m, const PcmSource &all, const float *feats_dev, const int64_t *frame_off,
+                   int n_utts, bool apply_cmvn, float *loglik, int32_t *argmax, cudaStream_t s, bool contexted) {
   if (apply_cmvn && !m->has_cmvn) {
     SetError("the model was loaded without CMVN statistics");
     return CE_GPU_EINVAL;

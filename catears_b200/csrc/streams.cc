@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <vector>
 
@@ -40,6 +41,9 @@ struct ce_gpu_streams {
   PinnedBuf pcm_host;
   DevBuf pcm_new, wave, raw, cm_in, cm_state, norm, x, ll, rows_stage;
   Table segs, fbank_chunks, cmvn_utts;
+  // host time spent inside ce_gpu_streams_process (ce_gpu_streams_call_stats)
+  int64_t stat_calls = 0;
+  double stat_enqueue_us = 0, stat_total_us = 0;
 
   size_t rem_stride() const { return kFrameLen; }                          // int16
   size_t hist_stride() const { return (size_t)kCmvnWindow * mel; }         // float
@@ -144,6 +148,21 @@ int ce_gpu_streams_open(ce_gpu_streams_t *S) {
   return CE_GPU_ENOMEM;
 }
 
+int ce_gpu_streams_call_stats(ce_gpu_streams_t *S, int64_t *calls, double *enqueue_us, double *total_us, int reset) {
+  if (!S) {
+    SetError("ce_gpu_streams_call_stats: null set");
+    return CE_GPU_EINVAL;
+  }
+  if (calls) *calls = S->stat_calls;
+  if (enqueue_us) *enqueue_us = S->stat_enqueue_us;
+  if (total_us) *total_us = S->stat_total_us;
+  if (reset) {
+    S->stat_calls = 0;
+    S->stat_enqueue_us = S->stat_total_us = 0;
+  }
+  return CE_GPU_OK;
+}
+
 int64_t ce_gpu_streams_rows_ready(const ce_gpu_streams_t *S, const int *slots, int n, const int *n_samples,
                                   const unsigned char *end_of_stream) {
   if (!S || n < 0 || (n > 0 && (!slots || !n_samples))) {
@@ -166,6 +185,8 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
   }
   if (row_offsets) row_offsets[0] = 0;
   if (n == 0) return CE_GPU_OK;
+  auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   ce_gpu_model *m = S->model;
   const int L = m->left, R = m->right, mel = S->mel, W = m->out_words();
   std::vector<Plan> plan;
@@ -379,6 +400,7 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
     CE_CHECK(NnetForward(m, S->x.as<float>(), xoff.data(), (int)ready_idx.size(), /*apply_cmvn=*/false,
                          S->ll.as<float>(), nullptr, s, /*contexted=*/true));   // blocks carry their context
   CE_CHECK(run(g5, g6));
+  const double t_enqueued = now();                         // everything but the rows' way home is queued
   if (rows_host && rows_total > 0)
     CE_CUDA(cudaMemcpyAsync(rows, rows_dev, sizeof(float) * (size_t)rows_total * W, cudaMemcpyDeviceToHost, s));
 
@@ -396,6 +418,9 @@ int ce_gpu_streams_process(ce_gpu_streams_t *S, const int *slots, int n, const i
     if (end_of_stream && end_of_stream[i]) st = ce_gpu_streams::Slot();   // free again
   }
   if (rows_host) CE_CUDA(cudaStreamSynchronize(s));        // host rows are complete on return
+  S->stat_calls += 1;
+  S->stat_enqueue_us += t_enqueued - t_start;
+  S->stat_total_us += now() - t_start;
   return CE_GPU_OK;
 }
 

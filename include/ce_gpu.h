@@ -226,6 +226,13 @@ int ce_gpu_streams_process(ce_gpu_streams_t *s, const int *slots, int n, const i
                            const int *n_samples, const unsigned char *end_of_stream, float *rows,
                            int64_t rows_cap, int64_t *row_offsets, void *stream);
 
+/* Host time spent inside ce_gpu_streams_process since the set was created (or the last reset), in
+ * microseconds: until all work of a call was queued (`enqueue_us`: planning, the PCM upload, ~40 kernel
+ * launches) and until the call returned (`total_us`: + waiting for the rows to arrive in a host buffer).
+ * Any out pointer may be NULL. */
+int ce_gpu_streams_call_stats(ce_gpu_streams_t *s, int64_t *calls, double *enqueue_us, double *total_us,
+                              int reset);
+
 /* Debug/parity hook (int8 models): after the next ce_gpu_nnet/ce_gpu_forward call the int32
  * accumulators of the `linear_ordinal`-th Linear layer are kept; fetch them with
  * ce_gpu_nnet_get_acc.  Pass -1 to disable. */

@@ -101,3 +101,30 @@ def test_null_handles_are_rejected_not_dereferenced():
     off = (C.c_int64 * 2)()
     assert L.ce_gpu_streams_process(None, slots, 1, None, cnt, None, None, 0, off, None) < 0
     L.ce_gpu_streams_free(None)                              # like free(NULL)
+
+
+def test_corrupt_model_files_are_errors_not_crashes(tmp_path):
+    """Header dimensions a file cannot back (2^31-ish rows, truncated data) come back as a load error
+    with a message -- no allocation is driven by them and no C++ exception crosses the C ABI."""
+    import struct
+
+    import numpy as np
+    from catears_b200 import formats as F
+    prior = str(tmp_path / "p.prior")
+    F.write_vector(prior, np.full(8, 0.125, np.float32))
+    good = str(tmp_path / "good.nnet")
+    F.write_nnet(good, [{"type": F.LINEAR, "W": np.zeros((40, 8), np.float32), "b": np.zeros(8, np.float32)}], 0, 0)
+    data = open(good, "rb").read()
+    cases = {
+        "huge_mat": data[:16] + b"LAY0" + struct.pack("<i", 0) + b"MAT0" + struct.pack("<iii", 8, 2000000000, 2000000000),
+        "huge_vec": data[:16] + b"LAY0" + struct.pack("<i", 7) + b"VEC0" + struct.pack("<ii", 4 * 500000000 + 4, 500000000),
+        "truncated": data[:len(data) // 2],
+        "bad_magic": b"XXXX" + data[4:],
+        "splice_neg": data[:16] + b"LAY0" + struct.pack("<ii", 6, -5),
+    }
+    for name, blob in cases.items():
+        path = str(tmp_path / (name + ".nnet"))
+        open(path, "wb").write(blob)
+        with pytest.raises(api.CeGpuError):
+            api.AcousticModelGpu(nnet=path, prior=prior)
+        assert api.last_error() != ""
