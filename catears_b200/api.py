@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libce_gpu.so")
+# CE_GPU_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("CE_GPU_LIB") or os.path.join(_HERE, "libce_gpu.so")
 
 PRECISION_INT8, PRECISION_BF16, PRECISION_FP32, PRECISION_TF32, PRECISION_BF16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"int8": 0, "bf16": 1, "fp32": 2, "tf32": 3, "bf16x3": 4}

@@ -35,10 +35,21 @@ namespace {
 constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB: 128 rows of A per CTA per stage
 constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quadrant (column halves)
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreads = 64 + kEpiThreads;               // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kThreads = 64 + kEpiThreads + 32;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue,
+                                                         // warp 10 the epilogue's parameter prefetcher
 constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
-constexpr int kParamBytes = 7 * kTileN * 4;              // bias, bn scale, bn offset, int correction (x4
-                                                         // in granule mode: one per 32-row quadrant)
+// Per-tile epilogue parameters, staged by the prefetch warp one tile ahead (two slots): bias, bn scale,
+// bn offset, the per-column integer correction (x4 in granule mode: one per 32-row quadrant), then per
+// accumulator row of this CTA the row's integer correction and its FindMinMax flag, then per quadrant
+// c_scale and the utterance.
+constexpr int kParamCols = 7 * kTileN;                   // words of per-column arrays
+constexpr int kParamRowCorr = kParamCols;                // int32[128]
+constexpr int kParamRowFlag = kParamRowCorr + kTileM;    // int32[128]
+constexpr int kParamScale = kParamRowFlag + kTileM;      // float[4]
+constexpr int kParamUtt = kParamScale + 4;               // int32[4]
+constexpr int kParamSlotWords = kParamUtt + 4 + 24;      // padded to a multiple of 32 words
+constexpr int kParamSlots = 2;
+constexpr int kParamBytes = kParamSlots * kParamSlotWords * 4;
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
 
@@ -58,7 +69,7 @@ struct Cfg {
   static constexpr int kOffBars = kOffParams + kParamBytes;
   static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kOffBars + 256;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
-  static_assert(2 * kStages + 2 * kAccStages + 1 <= 32, "barrier block");
+  static_assert(2 * kStages + 2 * kAccStages + 2 * kParamSlots + 1 <= 32, "barrier block");
 };
 
 // ---------------------------------------------------------------------------
@@ -123,9 +134,6 @@ __device__ __forceinline__ void tma_store_wait_all() {
 }
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void epi_bar() {               // the 256 epilogue threads only
-  asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 // ---- cluster (cta_group::2) helpers ----
@@ -323,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   unsigned char *smem_a = smem;                                   // [kStages][kABytes]
   unsigned char *smem_b = smem + kStages * kABytes;               // [kStages][kBBytes]
   unsigned char *smem_out = smem + C::kOffStage;                  // [kEpiWarps][kOutTileBytes]
-  float *sp = reinterpret_cast<float *>(smem + C::kOffParams);    // [4][kTileN]
+  float *sp_all = reinterpret_cast<float *>(smem + C::kOffParams);   // [kParamSlots][kParamSlotWords]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::kOffBars);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot.
   // With CG == 2 the same block exists in both CTAs; `full` and `tmem_empty` are used in the
@@ -332,7 +340,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const uint32_t bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages);
   const uint32_t bar_tempty = smem_u32(bars + 2 * kStages + kAccStages);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kAccStages);
+  const uint32_t bar_pfull = smem_u32(bars + 2 * kStages + 2 * kAccStages);      // parameter slots
+  const uint32_t bar_pempty = bar_pfull + 8 * kParamSlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kAccStages + 2 * kParamSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -349,6 +359,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, kEpiWarps * CG);
+    }
+    for (int i = 0; i < kParamSlots; ++i) {
+      mbar_init(bar_pfull + 8 * i, 1);
+      mbar_init(bar_pempty + 8 * i, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -471,19 +485,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
     const int half = ew >> 2;                            // which 128 of the tile's 256 columns
-    const int et = threadIdx.x - 64;                     // 0..255
     unsigned char *stg = smem_out + ew * kOutTileBytes;
     const uint32_t stg_u32 = smem_u32(stg);
     const int flags = (p.relu ? 1 : 0) | (p.bn_scale ? 2 : 0) | (p.minmax ? 4 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int pslot = 0;                                       // parameter slot of the tile being drained
+    uint32_t pphase = 0;
+    // CE_GPU_GEMM_PROF: where an epilogue warp's cycles go, summed over the grid into p.dbg[0..7]:
+    // waiting for parameters, waiting for a full accumulator, tcgen05.ld, math, staging + store, the tile's
+    // tail (TMEM hand-back, min/max reduction), the whole loop, tiles
+    // (compiled in only with -DCE_GEMM_PROF: the counters cost the epilogue registers)
+#ifdef CE_GEMM_PROF
+    const bool prof_on = p.dbg != nullptr;
+#else
+    constexpr bool prof_on = false;
+#endif
+    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long pr_t0 = prof_on ? clock64() : 0;
     const uint32_t tempty0 = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
-    const int n_gran = (p.M + kRowGran - 1) / kRowGran;
     // granule mode: every 32-row quadrant of the tile may belong to another utterance, so the
     // per-column integer correction (it contains the utterance's zero point) exists once per quadrant
     const int corr_off = (3 + (GRAN ? quad : 0)) * kTileN;
@@ -492,82 +517,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * kTileN;
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
 
-      // ---- per-tile constants; per-column parameters -> shared memory ----
-      // (the independent loads first, so that they are in flight under the dependent
-      // tile -> utterance -> parameters chain and the barrier below)
-      int32_t rs = 0, rs1 = 0, rs2 = 0;                  // three loads in flight; summed after the barrier
-      if (KIND == kKindI8) {
-        const int r0 = my_row + p.tap_off[0];
-        if (r0 >= 0 && r0 < p.M) rs = __ldg(p.a_rowsum + r0);
-        if (p.n_taps > 1) {
-          const int r1 = my_row + p.tap_off[1];
-          if (r1 >= 0 && r1 < p.M) rs1 = __ldg(p.a_rowsum + r1);
-        }
-        if (p.n_taps > 2) {
-          const int r2 = my_row + p.tap_off[2];
-          if (r2 >= 0 && r2 < p.M) rs2 = __ldg(p.a_rowsum + r2);
-        }
-        for (int t = 3; t < p.n_taps; ++t) {
-          const int r = my_row + p.tap_off[t];
-          if (r >= 0 && r < p.M) rs1 += __ldg(p.a_rowsum + r);
-        }
-      }
-      const int pcol_param = n0 + et;                    // parameter arrays are padded to kTileN
-      const float bias_v = p.bias ? __ldg(p.bias + pcol_param) : 0.0f;
-      const float bns_v = p.bn_scale ? __ldg(p.bn_scale + pcol_param) : 1.0f;
-      const float bno_v = p.bn_offset ? __ldg(p.bn_offset + pcol_param) : 0.0f;
-      const int32_t colsum_v = (KIND == kKindI8) ? __ldg(p.b_colsum + pcol_param) : 0;
-      const int utt = p.tile_utt ? p.tile_utt[min(m0 / kRowGran + (GRAN ? quad : 0), n_gran - 1)] : 0;
-      int32_t zp_a = 0;
+      // ---- per-tile parameters: staged one tile ahead by the prefetch warp (no global load and no CTA
+      //      barrier on this path: the dependent tile -> utterance -> parameters loads used to cost the
+      //      epilogue ~2.5 us a tile) ----
+      long long tq = prof_on ? clock64() : 0;
+      mbar_wait(bar_pfull + 8 * pslot, pphase);
+      if (prof_on) pr[0] += clock64() - tq;
+      const float *sp = sp_all + pslot * kParamSlotWords;
+      const int32_t *spi = reinterpret_cast<const int32_t *>(sp);
       RowConst rc;
-      rc.row_corr = 0;
-      rc.c_scale = 1.0f;
-      int32_t kzz = 0;
-      if (KIND == kKindI8) {
-        const QParam q = p.qa[utt];
-        zp_a = q.zero_point;
-        rc.c_scale = __fmul_rn(q.scale, p.scale_b);      // matrix.cc:403 (float * float)
-        kzz = p.k_true * zp_a * p.zp_b;
-      }
-      epi_bar();                                         // previous tile's parameters are no longer read
-      {
-        sp[et] = bias_v;
-        sp[kTileN + et] = bns_v;
-        sp[2 * kTileN + et] = bno_v;
-        if (!GRAN) {
-          reinterpret_cast<int32_t *>(sp)[3 * kTileN + et] = (KIND == kKindI8) ? kzz - zp_a * colsum_v : 0;
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int32_t zg = p.qa[p.tile_utt[min(m0 / kRowGran + g, n_gran - 1)]].zero_point;
-            reinterpret_cast<int32_t *>(sp)[(3 + g) * kTileN + et] = p.k_true * zg * p.zp_b - zg * colsum_v;
-          }
-        }
-      }
-      if (KIND == kKindI8) rc.row_corr = p.zp_b * (rs + rs1 + rs2);
-      bool use_row = false;                              // takes part in the fused FindMinMax
-      if (p.minmax) {
-        int pos = my_row, P = p.M;
-        if (p.utts) {
-          const UttRows ur = p.utts[utt];
-          pos = my_row - ur.row_off;
-          P = ur.rows;
-        }
-        if (pos >= p.mm_lo && pos < P - p.mm_hi) {
-          if (p.next_n_taps == 0) {
-            use_row = true;
-          } else {
-            for (int t = 0; t < p.next_n_taps; ++t) {
-              const int o = pos - p.next_tap_off[t];
-              if (o >= p.next_lo && o < P - p.next_hi) use_row = true;
-            }
-          }
-        }
-      }
+      rc.row_corr = spi[kParamRowCorr + quad * 32 + lane];
+      rc.c_scale = sp[kParamScale + (GRAN ? quad : 0)];
+      const int utt = spi[kParamUtt + (GRAN ? quad : 0)];
+      const bool use_row = spi[kParamRowFlag + quad * 32 + lane] != 0;   // takes part in the fused FindMinMax
       float vmin = FLT_MAX, vmax = -FLT_MAX;
-      epi_bar();                                         // parameters visible to all epilogue warps
 
+      tq = prof_on ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      if (prof_on) pr[1] += clock64() - tq;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * 128);
 
@@ -576,7 +543,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         const int col0 = n0 + pcol;
         if (col0 >= p.n_store) break;                    // warp-uniform
         uint32_t raw[32];
+        const long long tc0 = prof_on ? clock64() : 0;
         tmem_ld32(taddr + (uint32_t)(c * 32), raw);
+        const long long tc1 = prof_on ? clock64() : 0;
         if (p.debug & 1) continue;
         float v[32];
         float cmin = FLT_MAX, cmax = -FLT_MAX;           // this chunk's share of FindMinMax
@@ -612,6 +581,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         vmax = fmaxf(vmax, cmax);
 
         // ---- registers -> swizzled staging tile -> one TMA store per 32 x 128 B ----
+        const long long tc2 = prof_on ? clock64() : 0;
+        if (prof_on) {
+          pr[2] += tc1 - tc0;
+          pr[3] += tc2 - tc1;
+        }
         const int sw = lane & 7;
         if (KIND == kKindBF16X3 && p.out_bf16) {
           // the next layer's operand: 32 columns -> one 128-byte atom [32 hi | 32 lo] per row
@@ -685,12 +659,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             if (lane == 0) tma_store_2d(&map_o1, stg_u32, col0, m0 + quad * 32);
           }
         }
+        if (prof_on) pr[4] += clock64() - tc2;
       }
-      // accumulator drained: hand the TMEM stage back to the MMA warp
+      tq = prof_on ? clock64() : 0;
+      // accumulator drained: hand the TMEM stage back to the MMA warp, the parameter slot to the prefetcher
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(bar_tempty + 8 * acc); else mbar_arrive_cluster(tempty0 + 8 * acc);
+        mbar_arrive(bar_pempty + 8 * pslot);
+      }
+      if (++pslot == kParamSlots) {
+        pslot = 0;
+        pphase ^= 1;
       }
       if (++acc == kAccStages) {
         acc = 0;
@@ -712,8 +693,105 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           atomicMax(p.minmax + 2 * utt + 1, OrderedFromFloat(vmax));
         }
       }
+      if (prof_on) {
+        pr[5] += clock64() - tq;
+        pr[7] += 1;
+      }
     }
     if (lane == 0) tma_store_wait_all();                 // global writes done before the CTA exits
+    if (prof_on && lane == 0) {
+      pr[6] = clock64() - pr_t0;
+      for (int i = 0; i < 8; ++i) atomicAdd(p.dbg + i, (unsigned long long)pr[i]);
+    }
+  } else {
+    // ===================== parameter prefetcher (warp 10) =====================
+    // One tile ahead of the epilogue: everything its warps need per tile -- per-column bias /
+    // batch-norm / integer-correction arrays, per-row corrections and FindMinMax flags, per-quadrant
+    // scale and utterance -- goes into one of two shared-memory slots, signalled by an mbarrier.
+    const int n_gran = (p.M + kRowGran - 1) / kRowGran;
+    int pslot = 0;
+    uint32_t pphase = 0;
+    for (int tile = group_id; tile < total_tiles; tile += n_groups) {
+      const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
+      const int n0 = (tile % n_tiles) * kTileN;
+      mbar_wait(bar_pempty + 8 * pslot, pphase ^ 1);
+      float *sp = sp_all + pslot * kParamSlotWords;
+      int32_t *spi = reinterpret_cast<int32_t *>(sp);
+      // per quadrant (granule mode) or per tile: utterance and its activation quantisation
+      int utt_q[4];
+      int32_t zp_q[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        utt_q[g] = p.tile_utt ? __ldg(p.tile_utt + min(m0 / kRowGran + (GRAN ? g : 0), n_gran - 1)) : 0;
+        zp_q[g] = 0;
+      }
+      if (KIND == kKindI8) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!GRAN && g > 0) {
+            zp_q[g] = zp_q[0];
+            continue;
+          }
+          const QParam q = p.qa[utt_q[g]];
+          zp_q[g] = q.zero_point;
+          if (lane == g) sp[kParamScale + g] = __fmul_rn(q.scale, p.scale_b);   // matrix.cc:403 (float * float)
+        }
+      } else if (lane < 4) {
+        sp[kParamScale + lane] = 1.0f;
+      }
+      if (lane < 4) spi[kParamUtt + lane] = utt_q[lane];
+      // per column: 8 columns a lane (parameter arrays are padded to kTileN)
+#pragma unroll
+      for (int j = 0; j < kTileN / 32; ++j) {
+        const int c = lane + 32 * j;
+        sp[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.0f;
+        sp[kTileN + c] = p.bn_scale ? __ldg(p.bn_scale + n0 + c) : 1.0f;
+        sp[2 * kTileN + c] = p.bn_offset ? __ldg(p.bn_offset + n0 + c) : 0.0f;
+        const int32_t colsum = (KIND == kKindI8) ? __ldg(p.b_colsum + n0 + c) : 0;
+#pragma unroll
+        for (int g = 0; g < (GRAN ? 4 : 1); ++g)
+          spi[(3 + g) * kTileN + c] = (KIND == kKindI8) ? p.k_true * zp_q[g] * p.zp_b - zp_q[g] * colsum : 0;
+      }
+      // per row: 4 rows a lane, row group j = accumulator quadrant j
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = m0 + 32 * j + lane;
+        int32_t rsum = 0;
+        if (KIND == kKindI8) {
+          for (int t = 0; t < p.n_taps; ++t) {
+            const int r = row + p.tap_off[t];
+            if (r >= 0 && r < p.M) rsum += __ldg(p.a_rowsum + r);
+          }
+        }
+        spi[kParamRowCorr + 32 * j + lane] = p.zp_b * rsum;
+        int flag = 0;
+        if (p.minmax) {
+          int pos = row, P = p.M;
+          if (p.utts) {
+            const UttRows ur = p.utts[utt_q[GRAN ? j : 0]];
+            pos = row - ur.row_off;
+            P = ur.rows;
+          }
+          if (pos >= p.mm_lo && pos < P - p.mm_hi) {
+            if (p.next_n_taps == 0) {
+              flag = 1;
+            } else {
+              for (int t = 0; t < p.next_n_taps; ++t) {
+                const int o = pos - p.next_tap_off[t];
+                if (o >= p.next_lo && o < P - p.next_hi) flag = 1;
+              }
+            }
+          }
+        }
+        spi[kParamRowFlag + 32 * j + lane] = flag;
+      }
+      __syncwarp();                                      // every lane's stores before the arrive (release)
+      if (lane == 0) mbar_arrive(bar_pfull + 8 * pslot);
+      if (++pslot == kParamSlots) {
+        pslot = 0;
+        pphase ^= 1;
+      }
+    }
   }
 
   tc_fence_before();
@@ -930,6 +1008,31 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
     SetError("GemmLaunch: output row stride %lld is not a multiple of 4", (long long)args.ld_out);
     return CE_GPU_EINVAL;
   }
+  // built with -DCE_GEMM_PROF and run with CE_GPU_GEMM_PROF=1 (a debugging aid: synchronous, one line per
+  // launch): where the epilogue warps' time goes, averaged per warp
+#ifdef CE_GEMM_PROF
+  static const bool prof = getenv("CE_GPU_GEMM_PROF") != nullptr;
+#else
+  static const bool prof = false;
+#endif
+  static unsigned long long *prof_buf = nullptr;
+  if (prof) {
+    if (!prof_buf) CE_CUDA(cudaMalloc(&prof_buf, 64));
+    CE_CUDA(cudaMemsetAsync(prof_buf, 0, 64, s));
+    args.dbg = prof_buf;
+  }
+  struct ProfPrint {
+    bool on; cudaStream_t s; unsigned long long *buf; int M, N, taps;
+    ~ProfPrint() {
+      if (!on) return;
+      unsigned long long h[8];
+      if (cudaStreamSynchronize(s) != cudaSuccess || cudaMemcpy(h, buf, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+      const double w = 1965.0 * SmCount() * kEpiWarps;   // cycles -> us per epilogue warp (at the maximum clock)
+      fprintf(stderr, "gemm M %d N %d taps %d: epilogue warp us: loop %.1f = wait-params %.1f + wait-accumulator %.1f + "
+              "tcgen05.ld %.1f + math %.1f + stage/store %.1f + tail %.1f + rest; %.1f tiles\n", M, N, taps, h[6] / w,
+              h[0] / w, h[1] / w, h[2] / w, h[3] / w, h[4] / w, h[5] / w, (double)h[7] / (SmCount() * kEpiWarps));
+    }
+  } prof_print{prof, s, prof_buf, args.M, args.N, args.n_taps};
   static const int cta_group = getenv("CE_GPU_CTA_GROUP") ? atoi(getenv("CE_GPU_CTA_GROUP")) : 2;
   // granule mode only changes the int8 epilogue (the float kinds carry no per-utterance parameters)
   const bool gran = args.gran != 0 && kind == kKindI8 && args.tile_utt != nullptr;

@@ -93,6 +93,8 @@ struct GemmArgs {
   int32_t next_n_taps;           // 0: every valid row is used
   int32_t next_tap_off[kMaxTaps];
   int32_t next_lo, next_hi;      // next layer's valid output rows: [next_lo, P - next_hi)
+
+  unsigned long long *dbg;       // CE_GPU_GEMM_PROF: 8 cycle counters of the epilogue warps (gemm.cu), nullptr = off
 };
 
 struct GemmOperands {            // host-side description for the tensor maps
