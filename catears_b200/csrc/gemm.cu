@@ -24,8 +24,6 @@
 
 #include "gemm.h"
 
-#include "quant_math.cuh"
-
 #include <cuda_runtime.h>
 #include <float.h>
 
@@ -39,11 +37,6 @@ constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quad
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads + 32;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue,
                                                          // warp 10 the epilogue's parameter prefetcher
-// The int8 tile-layout instantiation adds warps 11..15, the fused quantiser (16 warps x 128 registers
-// is the whole register file of an SM).
-constexpr int kQuantWarps = 5;
-constexpr bool HasQuantWarps(int kind, bool gran) { return kind == kKindI8 && !gran; }
-constexpr int ThreadsOf(int kind, bool gran) { return kThreads + (HasQuantWarps(kind, gran) ? 32 * kQuantWarps : 0); }
 constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
 // Per-tile epilogue parameters, staged by the prefetch warp one tile ahead (two slots): bias, bn scale,
 // bn offset, the per-column integer correction (x4 in granule mode: one per 32-row quadrant), then per
@@ -350,8 +343,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const uint32_t bar_pfull = smem_u32(bars + 2 * kStages + 2 * kAccStages);      // parameter slots
   const uint32_t bar_pempty = bar_pfull + 8 * kParamSlots;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kAccStages + 2 * kParamSlots);
-  uint32_t *sig_cnt = tmem_slot + 2;                    // four arrival counters of the fused quantiser's reports
-                                                        // (epilogue warps are at most two tiles apart)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -373,7 +364,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       mbar_init(bar_pfull + 8 * i, 1);
       mbar_init(bar_pempty + 8 * i, kEpiWarps);
     }
-    sig_cnt[0] = sig_cnt[1] = sig_cnt[2] = sig_cnt[3] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -507,31 +497,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     uint32_t acc_phase = 0;
     int pslot = 0;                                       // parameter slot of the tile being drained
     uint32_t pphase = 0;
-    // fused Quantize (int8, tile layout): every epilogue warp confirms, one tile late (its stores were
-    // issued a whole tile ago, so the wait is free), that its share of a tile has been written; the last
-    // of the eight warps to confirm reports the CTA's 128 x 256 sub-tile to the utterance's counter with
-    // ONE gpu-scope fence, and the CTA that reports last for an utterance computes its
-    // QuantizationParams (src/matrix.cc:348-362) and publishes them with an 8-byte release store --
-    // the word the quantiser warps poll.
-    const bool fuse = HasQuantWarps(KIND, GRAN) && p.utt_done != nullptr;
-    int sig_utt = -1;                                    // utterance of the previous tile (not confirmed yet)
-    int sig_slot = 0;                                    // which of the four arrival counters it uses
-    auto confirm = [&](int u, int slot) {                // lane 0 of every epilogue warp, stores performed
-      uint32_t arrived;
-      asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(arrived) : "r"(smem_u32(sig_cnt + slot)) : "memory");
-      if (((arrived + 1u) & (uint32_t)(kEpiWarps - 1)) != 0u) return;   // (the counter only ever grows)
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      __threadfence();
-      const uint32_t old = atomicAdd(p.utt_done + u, 1u);
-      const int rows = p.utts ? p.utts[u].rows : p.M;
-      if (old + 1u == (uint32_t)(n_tiles * ((rows + kTileM - 1) / kTileM))) {
-        __threadfence();
-        const QParam qp = QParamsFromMinMax(__ldcg(p.minmax + 2 * u), __ldcg(p.minmax + 2 * u + 1));
-        const unsigned long long w =
-            (unsigned long long)__float_as_uint(qp.scale) | ((unsigned long long)(uint32_t)qp.zero_point << 32);
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p.q_params + u), "l"(w) : "memory");
-      }
-    };
     // CE_GPU_GEMM_PROF: where an epilogue warp's cycles go, summed over the grid into p.dbg[0..7]:
     // waiting for parameters, waiting for a full accumulator, tcgen05.ld, math, staging + store, the tile's
     // tail (TMEM hand-back, min/max reduction), the whole loop, tiles
@@ -551,7 +516,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
       const int n0 = (tile % n_tiles) * kTileN;
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
-      int n_stores = 0;                                  // TMA stores this warp issues for this tile
 
       // ---- per-tile parameters: staged one tile ahead by the prefetch warp (no global load and no CTA
       //      barrier on this path: the dependent tile -> utterance -> parameters loads used to cost the
@@ -681,7 +645,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           fence_async_smem();
           __syncwarp();
           if (lane == 0) tma_store_2d(&map_o0, stg_u32, col0, m0 + quad * 32);
-          ++n_stores;
           if (KIND == kKindTF32 && p.out_lo) {           // 3xTF32 consumers: the exact remainder
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -730,108 +693,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           atomicMax(p.minmax + 2 * utt + 1, OrderedFromFloat(vmax));
         }
       }
-      if (fuse) {                                        // the previous tile's stores: all but this tile's n_stores
-        if (lane == 0 && sig_utt >= 0) {
-          switch (n_stores) {
-            case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
-            case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
-            case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
-            case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
-            default: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
-          }
-          confirm(sig_utt, sig_slot);
-        }
-        sig_utt = (m0 < p.M) ? utt : -1;
-        sig_slot = (sig_slot + 1) & 3;
-      }
       if (prof_on) {
         pr[5] += clock64() - tq;
         pr[7] += 1;
       }
     }
     if (lane == 0) tma_store_wait_all();                 // global writes done before the CTA exits
-    if (fuse && lane == 0 && sig_utt >= 0) confirm(sig_utt, sig_slot);   // the last tile's report
     if (prof_on && lane == 0) {
       pr[6] = clock64() - pr_t0;
       for (int i = 0; i < 8; ++i) atomicAdd(p.dbg + i, (unsigned long long)pr[i]);
     }
-  } else if (HasQuantWarps(KIND, GRAN) && warp > 2 + kEpiWarps) {
-    // ===================== fused quantiser (warps 11..15) =====================
-    // Quantize (src/matrix.cc:366-387) of this GEMM's result for the next layer, by the same kernel: rows
-    // are dealt round-robin to the quantiser warps of the whole grid, so every finished utterance is
-    // converted by all SMs at once, right behind the tiles that produced it (its fp32 rows are read
-    // back through L2).  Software pipeline per warp: the row being converted, the next row's loads in
-    // flight, and the poll of the row after that already issued.
-    if (p.q_out != nullptr) {
-      constexpr int NV = 8;                              // 8 x 128 columns: q_cpad <= 1024
-      constexpr unsigned long long kNotYet = ~0ull;      // q_params[utt] before the utterance is complete
-      const int qw = warp - (3 + kEpiWarps);
-      const int G = (int)gridDim.x * kQuantWarps;
-      const int C = p.N, c_pad = p.q_cpad;
-      auto peek = [&](int row) -> unsigned long long {   // warp-uniform; kNotYet = not complete yet
-        const int utt = p.tile_utt ? __ldg(p.tile_utt + row / kRowGran) : 0;
-        unsigned long long v;
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.q_params + utt) : "memory");
-        return v;
-      };
-      auto wait_params = [&](int row) -> unsigned long long {
-        unsigned long long v = peek(row);
-        if (v != kNotYet) return v;
-        const long long t0 = clock64();
-        while ((v = peek(row)) == kNotYet) {
-          __nanosleep(1024);
-          if (clock64() - t0 > 20000000000LL) __trap();
-        }
-        return v;
-      };
-      auto load_row = [&](int row, float4 (&buf)[NV]) {
-        const float4 *r4 = reinterpret_cast<const float4 *>(p.out_f32 + (int64_t)row * p.ld_out);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          const int c4 = (i * 32 + lane) * 4;
-          buf[i] = (c4 < C) ? __ldcg(r4 + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      float4 cur[NV], nxt[NV];
-      int row = (int)blockIdx.x * kQuantWarps + qw;
-      if (row < p.M) {
-        unsigned long long pc = wait_params(row);
-        load_row(row, cur);
-        int row_n = row + G;
-        unsigned long long pn = row_n < p.M ? peek(row_n) : kNotYet;
-        while (true) {
-          bool have_next = false;
-          unsigned long long pnn = kNotYet;
-          if (row_n < p.M && pn != kNotYet) {            // next row: loads in flight under this row's math
-            load_row(row_n, nxt);
-            have_next = true;
-            if (row_n + G < p.M) pnn = peek(row_n + G);
-          }
-          QParam qp;
-          qp.scale = __uint_as_float((uint32_t)pc);
-          qp.zero_point = (int32_t)(uint32_t)(pc >> 32);
-          const QuantConst k = MakeQuantConst(qp);
-          uint32_t *o = reinterpret_cast<uint32_t *>(p.q_out + (int64_t)row * c_pad);
-          int32_t sum = k.fast ? QuantRow<NV, true>(cur, k, C, c_pad, lane, o) : QuantRow<NV, false>(cur, k, C, c_pad, lane, o);
-#pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sft);
-          if (lane == 0) p.q_rowsum[row] = sum;
-          if (row_n >= p.M) break;
-          if (!have_next) {
-            pn = wait_params(row_n);
-            load_row(row_n, nxt);
-            if (row_n + G < p.M) pnn = peek(row_n + G);
-          }
-#pragma unroll
-          for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
-          pc = pn;
-          pn = pnn;
-          row = row_n;
-          row_n += G;
-        }
-      }
-    }
-  } else if (warp == 2 + kEpiWarps) {
+  } else {
     // ===================== parameter prefetcher (warp 10) =====================
     // One tile ahead of the epilogue: everything its warps need per tile -- per-column bias /
     // batch-norm / integer-correction arrays, per-row corrections and FindMinMax flags, per-quadrant
@@ -1097,7 +969,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(ThreadsOf(KIND, GRAN));
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -84,9 +84,7 @@ struct GemmArgs {
   int32_t round_tf32;            // out_f32 = tf32-rounded value (so that out_lo is exact)
   int32_t debug;                 // CE_GPU_GEMM_DEBUG bits (timing probes only, results are WRONG):
                                  // 1 = epilogue drains TMEM but skips math and stores,
-                                 // 2 = no tcgen05.mma is issued, 4 = no TMA loads are issued,
-                                 // 8 = fused quantiser off inside the kernel, 16 = quantiser warps load rows but
-                                 // convert nothing, 32 = completion signals without the store-completion wait and fences
+                                 // 2 = no tcgen05.mma is issued, 4 = no TMA loads are issued
 
   // fused FindMinMax (src/matrix.cc:329-345) for the next layer's Quantize: only rows the next
   // layer's Splice+Narrow actually reads take part.
@@ -96,17 +94,6 @@ struct GemmArgs {
   int32_t next_tap_off[kMaxTaps];
   int32_t next_lo, next_hi;      // next layer's valid output rows: [next_lo, P - next_hi)
 
-  // fused Quantize (src/matrix.cc:366-387) of the result for the next layer -- int8, tile layout
-  // (gran == 0) only.  The kernel's quantiser warps wait until every tile of an utterance has been
-  // stored and its min/max reduced (utt_done), compute the utterance's QuantizationParams, read the
-  // utterance's fp32 rows back (they are still in L2) and write the next layer's u8 operand + row
-  // sums: the separate quantise launch and its HBM read of the fp32 activations disappear.
-  uint8_t *q_out;                // [M x q_cpad] u8 codes, zero padded; nullptr = off.  Must not alias A.
-  int32_t *q_rowsum;             // [M]
-  QParam *q_params;              // [n_utts] out: what the consuming GEMM's epilogue reads as qa; every
-                                 // entry all ones ("not computed yet") before the launch
-  int32_t q_cpad;                // multiple of 128, <= 1024
-  uint32_t *utt_done;            // [n_utts] completion counters, zero before the launch
   unsigned long long *dbg;       // CE_GPU_GEMM_PROF: 8 cycle counters of the epilogue warps (gemm.cu), nullptr = off
 };
 

@@ -20,8 +20,7 @@
 void ce_gpu_model::ChunkWs::Free() {
   x0.Free(); feats.Free(); fbank_chunks.Free();
   for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
-  for (int i = 0; i < 2; ++i) { act_u8[i].Free(); rowsum[i].Free(); }
-  logits.Free(); minmax.Free(); qparams.Free();
+  act_u8.Free(); rowsum.Free(); logits.Free(); minmax.Free(); qparams.Free();
   stage_loglik.Free();
   cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
   if (stream) cudaStreamDestroy(stream);
@@ -393,8 +392,8 @@ int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSour
   for (int i = 0; i < 2; ++i) CE_CHECK(w->act_f32[i].Reserve(sizeof(float) * (size_t)M * wmax));
   if (nb > 0) {
     if (m->kind == kKindI8) {
-      CE_CHECK(w->act_u8[0].Reserve((size_t)M * cmax));
-      CE_CHECK(w->rowsum[0].Reserve(sizeof(int32_t) * (size_t)M));
+      CE_CHECK(w->act_u8.Reserve((size_t)M * cmax));
+      CE_CHECK(w->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
       CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
       CE_CHECK(w->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
       CE_CHECK(InitMinMaxLaunch(w->minmax.as<uint32_t>(), nb * n_utts, s));
@@ -476,10 +475,10 @@ int ForwardChunkGeneral(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSour
           use.lo = st.lo;
           use.hi = st.hi;
           CE_CHECK(MinMaxLaunch(cur, ld, dim, M, rs.d_tile, rs.d_utts, use, mm, s));
-          CE_CHECK(QuantizeLaunch(cur, ld, dim, M, D.c_pad, rs.d_tile, mm, n_utts, qp, w->act_u8[0].as<uint8_t>(),
-                                  w->rowsum[0].as<int32_t>(), s));
-          ops.a[0] = w->act_u8[0].ptr;
-          a.a_rowsum = w->rowsum[0].as<int32_t>();
+          CE_CHECK(QuantizeLaunch(cur, ld, dim, M, D.c_pad, rs.d_tile, mm, n_utts, qp, w->act_u8.as<uint8_t>(),
+                                  w->rowsum.as<int32_t>(), s));
+          ops.a[0] = w->act_u8.ptr;
+          a.a_rowsum = w->rowsum.as<int32_t>();
           a.b_colsum = D.colsum.as<int32_t>();
           a.zp_b = D.zp_b;
           a.scale_b = D.scale_b;
@@ -565,11 +564,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   CE_CHECK(w->logits.Reserve(sizeof(float) * (size_t)M * ldp));
   if (m->kind == kKindI8) {
     CE_CHECK(w->act_f32[0].Reserve(sizeof(float) * (size_t)M * wmax));
-    for (int i = 0; i < 2; ++i) {
-      CE_CHECK(w->act_u8[i].Reserve((size_t)M * wmax));
-      CE_CHECK(w->rowsum[i].Reserve(sizeof(int32_t) * (size_t)M));
-    }
-    CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 3 * (size_t)nb * n_utts));
+    CE_CHECK(w->act_u8.Reserve((size_t)M * wmax));
+    CE_CHECK(w->rowsum.Reserve(sizeof(int32_t) * (size_t)M));
+    CE_CHECK(w->minmax.Reserve(sizeof(uint32_t) * 2 * (size_t)nb * n_utts));
     CE_CHECK(w->qparams.Reserve(sizeof(QParam) * (size_t)nb * n_utts));
   } else if (m->kind == kKindBF16 || m->kind == kKindBF16X3) {
     for (int i = 0; i < 2; ++i)
@@ -584,8 +581,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   // ---- fbank (when the input is PCM), replicate padding (+ CMVN) into x0, first min/max ----
   uint32_t *mm = w->minmax.as<uint32_t>();
   QParam *qp = w->qparams.as<QParam>();
-  uint32_t *done = mm + 2 * (size_t)nb * n_utts;          // completion counters of the fused quantiser
-  if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s, done, qp));
+  HostMark("chunk: reserve");
+  if (m->kind == kKindI8) CE_CHECK(InitMinMaxLaunch(mm, nb * n_utts, s));
+  HostMark("chunk: init minmax");
   CE_CHECK(ChunkInput(m, w, src, feats_dev, frame_off, n_utts, apply_cmvn, rs, m->kind == kKindI8 ? mm : nullptr, s,
                       contexted));
 
@@ -594,7 +592,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   const int c0 = m->blocks[0].c_pad;
   if (m->kind == kKindI8) {
     CE_CHECK(QuantizeLaunch(w->x0.as<float>(), F, F, M, c0, d_tile, mm, n_utts, qp,
-                            w->act_u8[0].as<uint8_t>(), w->rowsum[0].as<int32_t>(), s));
+                            w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
   } else if (m->kind == kKindBF16) {
     CE_CHECK(ConvertLaunch(w->x0.as<float>(), F, F, M, c0, w->act_bf16[0].as<__nv_bfloat16>(),
                            nullptr, nullptr, s));
@@ -642,11 +640,10 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
     ops.b[0] = D.w[0].ptr;
     ops.b[1] = D.w[1].ptr;
     const int next_c = last ? 0 : m->blocks[b + 1].c_pad;
-    bool fused_quant = false;
 
     if (m->kind == kKindI8) {
-      ops.a[0] = w->act_u8[b & 1].ptr;
-      a.a_rowsum = w->rowsum[b & 1].as<int32_t>();
+      ops.a[0] = w->act_u8.ptr;
+      a.a_rowsum = w->rowsum.as<int32_t>();
       a.b_colsum = D.colsum.as<int32_t>();
       a.zp_b = D.zp_b;
       a.scale_b = D.scale_b;
@@ -662,16 +659,6 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         a.next_n_taps = ru.next_n_taps;
         memcpy(a.next_tap_off, ru.next_tap_off, sizeof(a.next_tap_off));
         a.next_lo = ru.next_lo; a.next_hi = ru.next_hi;
-        // Quantize for the next layer by the GEMM's own quantiser warps (tile layout, rows <= 1024 wide)
-        static const bool fuse_env = !(getenv("CE_GPU_FUSED_QUANT") && atoi(getenv("CE_GPU_FUSED_QUANT")) == 0);
-        fused_quant = fuse_env && !gran && next_c % 128 == 0 && next_c <= 1024 && a.N % 4 == 0;
-        if (fused_quant) {
-          a.q_out = w->act_u8[(b + 1) & 1].as<uint8_t>();
-          a.q_rowsum = w->rowsum[(b + 1) & 1].as<int32_t>();
-          a.q_params = qp + (size_t)(b + 1) * n_utts;
-          a.q_cpad = next_c;
-          a.utt_done = done + (size_t)(b + 1) * n_utts;
-        }
       }
       if (m->keep_acc == b) {
         CE_CHECK(m->acc_dump.Reserve(sizeof(int32_t) * (size_t)M * a.ld_out));
@@ -726,11 +713,11 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
       CE_CUDA(cudaStreamWaitEvent(s, w->to_lo, 0));
     }
 
-    if (m->kind == kKindI8 && !last && !fused_quant) {
+    if (m->kind == kKindI8 && !last) {
       QParam *q_next = qp + (size_t)(b + 1) * n_utts;
       CE_CHECK(QuantizeLaunch(w->act_f32[0].as<float>(), a.ld_out, a.N, M, next_c, d_tile,
                               mm + 2 * (size_t)(b + 1) * n_utts, n_utts, q_next,
-                              w->act_u8[(b + 1) & 1].as<uint8_t>(), w->rowsum[(b + 1) & 1].as<int32_t>(), s));
+                              w->act_u8.as<uint8_t>(), w->rowsum.as<int32_t>(), s));
     }
   }
 

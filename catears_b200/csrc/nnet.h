@@ -61,9 +61,8 @@ struct ce_gpu_model {
     ce::DevBuf feats;                  // this chunk's fbank output [frames x feat_dim]
     ce::Table fbank_chunks;
     ce::DevBuf x0;                     // padded fp32 input [M x feat_dim]
-    ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8[2], rowsum[2], logits;
-    ce::DevBuf minmax, qparams;       // minmax: [blocks][utts][2] ordered min/max, then [blocks][utts]
-                                       // completion counters of the fused quantiser
+    ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits;
+    ce::DevBuf minmax, qparams;
     ce::DevBuf stage_loglik;
     ce::Table cmvn_utts, utt_table, tile_table, outrow_table;
     // `stream` (low priority) carries the memory-bound kernels, `stream_hi` (high priority) the

@@ -9,8 +9,6 @@
 //                     + "row -= log_prior" src/am.cc:109-112 + argmax, written as compact rows
 #include "nnet_kernels.h"
 
-#include "quant_math.cuh"
-
 #include <float.h>
 
 #include <algorithm>
@@ -28,11 +26,9 @@ __device__ __forceinline__ bool RowUsed(int pos, int P, const RowUse &u) {
   return false;
 }
 
-__global__ void init_minmax_kernel(uint32_t *mm, int n, uint32_t *counters, unsigned long long *qparams) {
+__global__ void init_minmax_kernel(uint32_t *mm, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    if (counters) counters[i] = 0u;
-    if (qparams) qparams[i] = ~0ull;                     // "not computed yet" (the fused quantiser polls it)
     mm[2 * i] = OrderedFromFloat(FLT_MAX);               // matrix.cc:330
     mm[2 * i + 1] = OrderedFromFloat(FLT_MIN);           // matrix.cc:331 (smallest positive normal)
   }
@@ -154,6 +150,79 @@ quantize_kernel(const float *__restrict__ x, int64_t ld_in, int C, int M, int c_
 constexpr int kQuantWarps = 4;
 constexpr int kQuantRowsPerWarp = 4;
 constexpr int kQuantUnitRows = kQuantWarps * kQuantRowsPerWarp;   // 16
+
+__device__ __forceinline__ QParam QParamsFromMinMax(const uint32_t *__restrict__ mm) {
+  const float mn = FloatFromOrdered(mm[0]);
+  const float mx = FloatFromOrdered(mm[1]);
+  const double scale = (double)__fsub_rn(mx, mn) / 255.0;             // matrix.cc:354
+  const double fzp = (double)(-mn) / scale;                           // matrix.cc:357
+  QParam q;
+  q.zero_point = (int32_t)round(fzp);                                 // matrix.cc:358
+  q.scale = (float)scale;                                             // matrix.cc:361
+  return q;
+}
+
+struct QuantConst {
+  float scale, inv, zp;
+  bool fast;          // scale is comfortably normal: the reciprocal path is exact
+};
+
+__device__ __forceinline__ QuantConst MakeQuantConst(const QParam p) {
+  QuantConst k;
+  k.scale = p.scale;
+  k.zp = (float)p.zero_point;
+  k.fast = p.scale > 1e-18f && p.scale < 1e18f;                       // false for NaN / denormal / inf
+  k.inv = k.fast ? __frcp_rn(p.scale) : 0.0f;
+  return k;
+}
+
+// RN(v / scale): q0 = RN(v * RN(1/scale)) is within 2 ulp; one residual step makes it faithful and
+// the second one correctly rounded (Markstein's theorem; the residuals are exact FMAs because
+// |v| <= 255 * scale * (1 + eps) keeps every term in the normal range, and for |v / scale| < 0.4
+// any last-bit error is absorbed by the rounding to an integer code).
+__device__ __forceinline__ float DivByScale(float v, const QuantConst &k) {
+  float q = __fmul_rn(v, k.inv);
+  float r = __fmaf_rn(-q, k.scale, v);
+  q = __fmaf_rn(r, k.inv, q);
+  r = __fmaf_rn(-q, k.scale, v);
+  return __fmaf_rn(r, k.inv, q);
+}
+
+// roundf(min(max(q, 0), 255)) as an int in [.., ..] BEFORE saturation: rounding half away from zero
+// commutes with the clamp (monotone, 0 and 255 are fixed points), truncating q + 0.49999997f is
+// round-half-away for 0 <= q < 2^23, negative / NaN inputs end at <= 0 and huge ones saturate.
+template <bool FAST>
+__device__ __forceinline__ int32_t CodeOf(float v, const QuantConst &k) {
+  const float d = FAST ? DivByScale(v, k) : __fdiv_rn(v, k.scale);    // matrix.cc:383
+  const float q = __fadd_rn(d, k.zp);
+  return __float2int_rz(__fadd_rn(q, 0.49999997f));                   // matrix.cc:384-385
+}
+
+__device__ __forceinline__ uint32_t PackCodes(int32_t a, int32_t b, int32_t c, int32_t d) {
+  uint32_t hi, w;   // bytes (low to high): a, b, c, d, each saturated to [0, 255]
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(b), "r"(a), "r"(hi));
+  return w;
+}
+
+// One row held in registers -> NV words of codes per lane; returns this lane's share of the row sum.
+template <int NV, bool FAST>
+__device__ __forceinline__ int32_t QuantRow(const float4 (&v)[NV], const QuantConst &k, int C, int c_pad,
+                                            int lane, uint32_t *__restrict__ o) {
+  int32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c4 = (j * 32 + lane) * 4;
+    uint32_t w = 0;
+    if (c4 < C) {
+      w = PackCodes(CodeOf<FAST>(v[j].x, k), CodeOf<FAST>(v[j].y, k), CodeOf<FAST>(v[j].z, k),
+                    CodeOf<FAST>(v[j].w, k));
+      sum = (int32_t)__dp4a(w, 0x01010101u, (uint32_t)sum);
+    }
+    if (c4 < c_pad) o[j * 32 + lane] = w;
+  }
+  return sum;
+}
 
 template <int NV>
 __global__ void __maxnreg__(96)
@@ -762,10 +831,10 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
 
 }  // namespace
 
-int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s, uint32_t *counters, QParam *qparams) {
+int InitMinMaxLaunch(uint32_t *mm, int n, cudaStream_t s) {
   if (n <= 0) return CE_GPU_OK;
   ProfScope prof(kProfQuantize, s);
-  init_minmax_kernel<<<(n + 255) / 256, 256, 0, s>>>(mm, n, counters, reinterpret_cast<unsigned long long *>(qparams));
+  init_minmax_kernel<<<(n + 255) / 256, 256, 0, s>>>(mm, n);
   CE_LAUNCHED();
   return CE_GPU_OK;
 }

@@ -15,10 +15,7 @@ struct RowUse {
   int32_t next_lo, next_hi;
 };
 
-// counters, qparams (nullable): n_pairs completion counters zeroed and n_pairs QParam entries set to
-// the "not computed yet" pattern in the same launch (GemmArgs::utt_done / q_params)
-int InitMinMaxLaunch(uint32_t *mm, int n_pairs, cudaStream_t s, uint32_t *counters = nullptr,
-                     QParam *qparams = nullptr);
+int InitMinMaxLaunch(uint32_t *mm, int n_pairs, cudaStream_t s);
 int MinMaxLaunch(const float *x, int64_t ld, int C, int M, const int32_t *tile_utt,
                  const UttRows *utts, const RowUse &use, uint32_t *minmax, cudaStream_t s);
 int QParamsLaunch(const uint32_t *minmax, QParam *q, int n, cudaStream_t s);
