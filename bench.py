@@ -521,7 +521,16 @@ def run_gpu(args):
     roofline_fbank = {"kernel": "fbank_kernel", "bound": "hbm", "achieved": round(fb_gbs, 1),
                       "peak": hbm_peak, "unit": "GB/s", "frac": round(fb_gbs / hbm_peak, 4),
                       "avg_launch_ms": round(fb_ms / max(1, fb_n), 4),
-                      "share_of_step": round(fb_ms / ms_serial, 4)}
+                      "share_of_step": round(fb_ms / ms_serial, 4),
+                      "frames_per_s": round(frames * args.steps / (fb_ms * 1e-3), 0) if fb_ms > 0 else None,
+                      "note": "an fp32 FFT at ~740 warp-instructions a frame is bound by issue slots and "
+                              "shared-memory wavefronts, not by HBM (DESIGN.md section 5): the fractions "
+                              "below are ncu's, of the same kernel at HEAD (profiles/traffic.json)"}
+    if os.path.exists(tr_path):
+        tr = json.load(open(tr_path))
+        if tr.get("fbank_issue_active_pct"):
+            roofline_fbank["issue_frac"] = round(tr["fbank_issue_active_pct"] / 100.0, 4)
+            roofline_fbank["smem_frac"] = round(tr["fbank_l1tex_throughput_pct"] / 100.0, 4)
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,

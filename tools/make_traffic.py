@@ -3,7 +3,8 @@
 utterances = one chunk of 131072 activation rows):
 
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
-sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none \
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,\
+l1tex__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none \
       -s <launches of the warm-up passes> -c <launches of one pass> --csv --log-file launches.csv \
       python tools/prof_one.py
 
@@ -40,6 +41,12 @@ def main():
     tr["step_%s_dram_bytes_per_row" % prec] = round(total / rows, 1)
     tr["kernels_%s" % prec] = {k: {"launches": c["launches"], "dram_bytes": int(c["dram_bytes"]), "us": round(c["us"], 1)}
                                for k, c in sorted(cats.items())}
+    # the fbank kernel is bound by issue slots and shared-memory wavefronts, not by HBM
+    for (_, k), d in per.items():
+        if k == "fbank_kernel":
+            tr["fbank_issue_active_pct"] = round(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0.0), 2)
+            tr["fbank_l1tex_throughput_pct"] = round(d.get("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", 0.0), 2)
+            tr["fbank_us_per_launch"] = round(d.get("gpu__time_duration.sum", 0.0), 1)
     g = cats.get("gemm_kernel")
     if g:
         tr["gemm_%s_dram_bytes_per_row" % prec] = round(g["dram_bytes"] / g["launches"] / rows, 1)
