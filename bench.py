@@ -374,9 +374,11 @@ def run_gpu(args):
             fn()
         e1.record(stream)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        local = e0.elapsed_time(e1)
+        ms = torch.tensor([local], device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        timed.local = local
         return float(ms.item())
 
     audio_per_step = world * n_utts * UTT_SECONDS
@@ -390,12 +392,24 @@ def run_gpu(args):
     if os.environ.get("BENCH_PROFILE_OVERLAP"):
         api.profile_enable(True)
     ms = timed(step_device, args.steps)
+    ms_local = timed.local
     if os.environ.get("BENCH_PROFILE_OVERLAP"):
         sys.stderr.write("overlapped per-kernel ms/step: %s\n" % {k: round(v[0] / args.steps, 3)
                                                                  for k, v in api.profile_read().items()})
         api.profile_enable(False)
     launches = api.launch_count()
     clocks = sampler.stop()
+    if world > 1:                                          # every rank watches its own GPU: slowest / fastest median
+        mhz = torch.tensor([clocks["sm_mhz"] or 0.0], device="cuda")
+        lo, hi = mhz.clone(), mhz.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        clocks["sm_mhz_min_over_ranks"] = float(lo.item())
+        clocks["sm_mhz_max_over_ranks"] = float(hi.item())
+        mine = torch.tensor([ms_local], device="cuda")
+        fastest = mine.clone()
+        dist.all_reduce(fastest, op=dist.ReduceOp.MIN)
+        clocks["ms_per_step_fastest_rank"] = round(float(fastest.item()) / args.steps, 3)
     value = audio_per_step * args.steps / (ms * 1e-3)
 
     # Per-kernel durations for the roofline: the same steps once more with CUDA events around
