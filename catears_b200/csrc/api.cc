@@ -65,7 +65,7 @@ const char *ce_gpu_last_error(void) { return LastError(); }
 
 int ce_gpu_device_count(void) { return DeviceCount(); }
 
-int ce_gpu_version(void) { return 100; }   // 0.1.0
+int ce_gpu_version(void) { return 200; }   // 0.2.0
 
 int64_t ce_gpu_launch_count(int reset) {
   int64_t v = LaunchCounter();
