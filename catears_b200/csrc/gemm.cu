@@ -33,16 +33,16 @@ namespace ce {
 namespace {
 
 constexpr int kABytes = kTileM * kTileKBytes;            // 16 KB: 128 rows of A per CTA per stage
-constexpr int kEpiWarps = 8;                             // 2 per TMEM lane quadrant (column halves)
-constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kThreads = 64 + kEpiThreads + 32;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue,
-                                                         // warp 10 the epilogue's parameter prefetcher
+// Warps of a CTA: warp 0 TMA, warp 1 MMA, then the epilogue warps (Cfg::kEpiWarps: 2 per TMEM lane
+// quadrant, one per column half of the tile; 4 per quadrant in the fused output layer, whose epilogue is
+// most of its work), then the epilogue's parameter prefetcher.
 constexpr int kOutTileBytes = 32 * 128;                  // 32 rows x 128 B staged per TMA store
 // Per-tile epilogue parameters, staged by the prefetch warp one tile ahead (two slots): bias, bn scale,
 // bn offset, the per-column integer correction (x4 in granule mode: one per 32-row quadrant), then per
 // accumulator row of this CTA the row's integer correction and its FindMinMax flag, then per quadrant
 // c_scale and the utterance.
-constexpr int kParamCols = 7 * kTileN;                   // words of per-column arrays
+constexpr int kParamCols = 8 * kTileN;                   // words of per-column arrays (slot 7: log prior, LSM)
+constexpr int kParamPrior = 7 * kTileN;
 constexpr int kParamRowCorr = kParamCols;                // int32[128]
 constexpr int kParamRowFlag = kParamRowCorr + kTileM;    // int32[128]
 constexpr int kParamScale = kParamRowFlag + kTileM;      // float[4]
@@ -50,6 +50,7 @@ constexpr int kParamUtt = kParamScale + 4;               // int32[4]
 constexpr int kParamSlotWords = kParamUtt + 4 + 24;      // padded to a multiple of 32 words
 constexpr int kParamSlots = 2;
 constexpr int kParamBytes = kParamSlots * kParamSlotWords * 4;
+constexpr int kXchgBytes = 2 * 4 * kTileM * 8;              // LSM: [stats | argmax][column part][row] 8-byte pairs
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
 
@@ -58,15 +59,22 @@ constexpr int kAccStages = 2;
 // and HALF of the B tile (128 of the 256 weight rows), so per CTA the L2 -> smem traffic and the
 // shared-memory operand reads of the tensor core drop by a third, and the smaller stages leave
 // room for a deeper ring.
-template <int CG>
+template <int CG, bool LSM = false>
 struct Cfg {
+  static constexpr int kEpiWarps = LSM ? 16 : 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps + 32;
+  static constexpr int kParts = kEpiWarps / 4;           // column parts of a tile, one epilogue warp each
+  static constexpr int kPartCols = kTileN / kParts;
+  static constexpr int kStgBytes = LSM ? 32 * 64 : kOutTileBytes;   // staging per epilogue warp
+  static constexpr int kMaxRegs = LSM ? 104 : 128;       // (2 + kEpiWarps + 1) warps x 32 x kMaxRegs <= 64 K
   static constexpr int kStages = (CG == 2) ? 5 : 3;
   static constexpr int kBRows = kTileN / CG;             // weight rows staged per CTA
   static constexpr int kBBytes = kBRows * kTileKBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOffStage = kStages * kStageBytes;   // output staging (1024-aligned)
-  static constexpr int kOffParams = kOffStage + kEpiWarps * kOutTileBytes;
-  static constexpr int kOffBars = kOffParams + kParamBytes;
+  static constexpr int kOffParams = kOffStage + kEpiWarps * kStgBytes;
+  static constexpr int kOffXchg = kOffParams + kParamBytes;    // LSM: row statistics / argmax exchange
+  static constexpr int kOffBars = kOffXchg + kXchgBytes;
   static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kOffBars + 256;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
   static_assert(2 * kStages + 2 * kAccStages + 2 * kParamSlots + 1 <= 32, "barrier block");
@@ -225,6 +233,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 columns, asynchronous: the registers are valid after tmem_ld16_wait (which names them, so
+// that no use can be scheduled above it).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                 "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
 // Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes,
 // 8-row groups 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -243,6 +272,36 @@ __device__ __forceinline__ uint32_t make_idesc() {
   const uint32_t ab_fmt = (KIND == kKindI8) ? 0u : (KIND == kKindTF32) ? 2u : 1u;   // U8, TF32, BF16
   return (c_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
          ((uint32_t)((kTileM * CG) >> 4) << 24);                      // M = 128 (one CTA) / 256 (pair)
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x: MUFU.EX2, tiny results flush to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Two fp32 operations in one instruction (sm_100 add / sub / mul / fma .f32x2): each half is an ordinary
+// IEEE round-to-nearest fp32 operation, so the results equal the scalar __fadd_rn / __fmul_rn chain.
+#define CE_F32X2_OP(NAME, OP)                                                                      \
+  __device__ __forceinline__ float2 NAME(float2 a, float2 b) {                                     \
+    float2 r;                                                                                      \
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"       \
+        OP " rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"                                           \
+        : "=f"(r.x), "=f"(r.y)                                                                     \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                 \
+    return r;                                                                                      \
+  }
+CE_F32X2_OP(add2, "add.rn.f32x2")
+CE_F32X2_OP(sub2, "sub.rn.f32x2")
+CE_F32X2_OP(mul2, "mul.rn.f32x2")
+#undef CE_F32X2_OP
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
 }
 
 __device__ __forceinline__ float round_tf32(float v) {
@@ -312,15 +371,140 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
 }
 
 // ---------------------------------------------------------------------------
+// fused output layer (LSM): 16 accumulator columns of one row at a time
+// ---------------------------------------------------------------------------
+// The layer's value in the reference's order of operations (as epi_math), two columns per instruction.
+template <int KIND>
+__device__ __forceinline__ void lsm_value(const uint32_t (&raw)[16], const float *sp, int corr_off, int pcol,
+                                          const RowConst rc, int flags, float neg_zero, float2 (&v2)[8]) {
+  const float2 nz2 = make_float2(neg_zero, neg_zero);
+  const float4 *b4 = reinterpret_cast<const float4 *>(sp + pcol);
+  const int4 *c4 = reinterpret_cast<const int4 *>(sp + corr_off + pcol);
+  const float2 sc2 = make_float2(rc.c_scale, rc.c_scale);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = b4[q];
+    float2 x0, x1;
+    if (KIND == kKindI8) {
+      const int4 cc = c4[q];
+      x0 = make_float2(__int2float_rn((int32_t)raw[4 * q] + (cc.x - rc.row_corr)),
+                       __int2float_rn((int32_t)raw[4 * q + 1] + (cc.y - rc.row_corr)));
+      x1 = make_float2(__int2float_rn((int32_t)raw[4 * q + 2] + (cc.z - rc.row_corr)),
+                       __int2float_rn((int32_t)raw[4 * q + 3] + (cc.w - rc.row_corr)));
+      // the product, rounded on its own (eight_bit_int_gemm.cc:389): x * s + (-0.0) is exactly RN(x * s).
+      // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 (and fma with a literal -0.0 + add) into ONE FFMA2,
+      // which would skip that rounding -- so the -0.0 comes from a kernel argument it cannot see through.
+      x0 = fma2(x0, sc2, nz2);
+      x1 = fma2(x1, sc2, nz2);
+    } else {
+      x0 = make_float2(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]));
+      x1 = make_float2(__uint_as_float(raw[4 * q + 2]), __uint_as_float(raw[4 * q + 3]));
+    }
+    v2[2 * q] = add2(x0, make_float2(bb.x, bb.y));                       // nnet.cc:34
+    v2[2 * q + 1] = add2(x1, make_float2(bb.z, bb.w));
+  }
+  if (flags & 3) {                                       // an output layer with ReLU / BatchNorm behind it
+    const float *bs = sp + kTileN + pcol, *bo = sp + 2 * kTileN + pcol;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x[2] = {v2[j].x, v2[j].y};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (flags & 1) asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(x[e]) : "f"(x[e]));   // nnet.cc:156
+        if (flags & 2) x[e] = __fadd_rn(__fmul_rn(x[e], bs[2 * j + e]), bo[2 * j + e]);    // nnet.cc:114-115
+      }
+      v2[j] = make_float2(x[0], x[1]);
+    }
+  }
+}
+
+__device__ __forceinline__ float max16(const float2 (&v2)[8]) {
+  const float p0 = fmaxf(fmaxf(v2[0].x, v2[0].y), fmaxf(v2[1].x, v2[1].y));
+  const float p1 = fmaxf(fmaxf(v2[2].x, v2[2].y), fmaxf(v2[3].x, v2[3].y));
+  const float p2 = fmaxf(fmaxf(v2[4].x, v2[4].y), fmaxf(v2[5].x, v2[5].y));
+  const float p3 = fmaxf(fmaxf(v2[6].x, v2[6].y), fmaxf(v2[7].x, v2[7].y));
+  return fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+}
+
+// First sweep: online log-sum-exp over the row's columns in the fixed order the tiles arrive in
+// (m: running maximum, s: sum of exp(x - m)); exp(x - m) = 2^(x log2e - m log2e), one FFMA and one
+// MUFU.EX2 per element.  n_ok (< 16 only in the last piece of a ragged row) is a multiple of 4.
+__device__ __forceinline__ void lsm_stats(float2 (&v2)[8], int n_ok, float &m, float &s) {
+  const float kLog2e = 1.4426950408889634f;
+  if (n_ok < 16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (2 * j >= n_ok) v2[j] = make_float2(-FLT_MAX, -FLT_MAX);
+  }
+  const float cmax = max16(v2);
+  if (cmax > m) {
+    s *= ex2_approx((m - cmax) * kLog2e);
+    m = cmax;
+  }
+  const float nm = -m * kLog2e;
+  const float2 nm2 = make_float2(nm, nm), l2 = make_float2(kLog2e, kLog2e);
+  float2 a[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 e = fma2(v2[j], l2, nm2);
+    a[j] = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 e = fma2(v2[4 + j], l2, nm2);
+    a[j] = add2(a[j], make_float2(ex2_approx(e.x), ex2_approx(e.y)));
+  }
+  const float2 t = add2(add2(a[0], a[1]), add2(a[2], a[3]));
+  s += t.x + t.y;
+}
+
+// Second sweep: the finished row (x - logsumexp) - log prior, and the row's first maximum.
+__device__ __forceinline__ void lsm_finish(float2 (&v2)[8], const float *prior, bool softmax, float lse, int n_ok,
+                                           int col0, float &best, int &best_i) {
+  const float4 *lp4 = reinterpret_cast<const float4 *>(prior);
+  const float2 lse2 = make_float2(lse, lse);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 lp = lp4[q];
+    float2 x0 = v2[2 * q], x1 = v2[2 * q + 1];
+    if (softmax) {                                                       // x -= max + log(sum)    vector.cc:120
+      x0 = sub2(x0, lse2);
+      x1 = sub2(x1, lse2);
+    }
+    v2[2 * q] = sub2(x0, make_float2(lp.x, lp.y));                       // AddVec(-1, log_prior_) am.cc:111
+    v2[2 * q + 1] = sub2(x1, make_float2(lp.z, lp.w));
+  }
+  if (n_ok < 16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (2 * j >= n_ok) v2[j] = make_float2(-FLT_MAX, -FLT_MAX);
+  }
+  // the piece's maximum first; its position only when it beats the row's best so far (first maximum wins:
+  // columns ascend, and only a strictly larger value replaces the best)
+  const float cmax = max16(v2);
+  if (cmax > best) {
+    best = cmax;
+    int at = 15;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      if (v2[j].y == cmax) at = 2 * j + 1;
+      if (v2[j].x == cmax) at = 2 * j;
+    }
+    best_i = col0 + at;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------
-template <int KIND, int CG, bool GRAN = false>
-__global__ void __maxnreg__(128)
+template <int KIND, int CG, bool GRAN = false, bool LSM = false>
+__global__ void __maxnreg__((Cfg<CG, LSM>::kMaxRegs))
 gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
             const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
             const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
             const GemmArgs p) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, LSM>;
+  constexpr int kEpiWarps = C::kEpiWarps;
   constexpr int kStages = C::kStages;
   constexpr int kBBytes = C::kBBytes;
   extern __shared__ unsigned char smem_raw[];
@@ -397,6 +581,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   const int kb_per_tap = p.c_pad / kTileK;
   const int steps_per_pass = p.n_taps * kb_per_tap;
   const int n_steps = p.n_pass * steps_per_pass;
+  // Work units.  Plain GEMM: one tile (m, n) per unit, units round-robin over the CTA groups.  LSM (the
+  // output layer fused with LogSoftmax / prior / argmax): one unit = ALL n tiles of one m tile, walked
+  // twice when the softmax is on -- a first sweep that only reduces every row's maximum and sum of
+  // exponentials, a second one that recomputes the accumulators and writes the finished rows -- so the
+  // logits never exist in memory.
+  const int n_units = LSM ? m_tiles : total_tiles;
+  const int n_subs = LSM ? (p.lsm_softmax ? 2 * n_tiles : n_tiles) : 1;
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own operand slices) ===============
@@ -404,9 +595,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full0 = (CG == 2) ? map_to_cta(bar_full, 0) : bar_full;   // leader's barriers
-      for (int tile = group_id; tile < total_tiles; tile += n_groups) {
-        const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;
-        const int n0 = (tile % n_tiles) * kTileN + (int)rank * C::kBRows;
+      for (int unit = group_id; unit < n_units; unit += n_groups)
+      for (int sub = 0; sub < n_subs; ++sub) {
+        const int mt = LSM ? unit : unit / n_tiles;
+        const int nt = LSM ? (sub >= n_tiles ? sub - n_tiles : sub) : unit % n_tiles;
+        const int m0 = mt * kGroupM + (int)rank * kTileM;
+        const int n0 = nt * kTileN + (int)rank * C::kBRows;
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const CUtensorMap *ma = p.pass_a[ps] ? &map_a1 : &map_a0;
           const CUtensorMap *mb = p.pass_b[ps] ? &map_b1 : &map_b0;
@@ -444,7 +638,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = group_id; tile < total_tiles; tile += n_groups) {
+      for (int unit = group_id; unit < n_units; unit += n_groups)
+      for (int sub = 0; sub < n_subs; ++sub) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileN);
@@ -489,8 +684,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     // ===================== epilogue (warps 2..9) =====================
     const int ew = warp - 2;
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                            // which 128 of the tile's 256 columns
-    unsigned char *stg = smem_out + ew * kOutTileBytes;
+    const int half = ew >> 2;                            // which part of the tile's 256 columns (128 each; LSM: 64)
+    unsigned char *stg = smem_out + ew * C::kStgBytes;
     const uint32_t stg_u32 = smem_u32(stg);
     const int flags = (p.relu ? 1 : 0) | (p.bn_scale ? 2 : 0) | (p.minmax ? 4 : 0);
     int acc = 0;
@@ -512,9 +707,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     // granule mode: every 32-row quadrant of the tile may belong to another utterance, so the
     // per-column integer correction (it contains the utterance's zero point) exists once per quadrant
     const int corr_off = (3 + (GRAN ? quad : 0)) * kTileN;
-    for (int tile = group_id; tile < total_tiles; tile += n_groups) {
-      const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
-      const int n0 = (tile % n_tiles) * kTileN;
+    // LSM: the row's running maximum / sum of exponentials (first sweep), its log-sum-exp and the best
+    // (value, pdf) so far (second sweep); both column halves of a row meet through shared memory
+    float lsm_m = -FLT_MAX, lsm_s = 0.0f, lsm_lse = 0.0f, lsm_best = -FLT_MAX;
+    int lsm_best_i = 0x7fffffff;
+    float2 *xchg_stats = reinterpret_cast<float2 *>(smem + C::kOffXchg);            // [4][kTileM]
+    float2 *xchg_best = xchg_stats + 4 * kTileM;                                    // [4][kTileM]
+    for (int unit = group_id; unit < n_units; unit += n_groups)
+    for (int sub = 0; sub < n_subs; ++sub) {
+      const int mt = LSM ? unit : unit / n_tiles;
+      const int nt = LSM ? (sub >= n_tiles ? sub - n_tiles : sub) : unit % n_tiles;
+      const int m0 = mt * kGroupM + (int)rank * kTileM;  // this CTA's 128 rows
+      const int n0 = nt * kTileN;
       const int my_row = m0 + quad * 32 + lane;          // the accumulator row this thread reads
 
       // ---- per-tile parameters: staged one tile ahead by the prefetch warp (no global load and no CTA
@@ -529,15 +733,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       rc.row_corr = spi[kParamRowCorr + quad * 32 + lane];
       rc.c_scale = sp[kParamScale + (GRAN ? quad : 0)];
       const int utt = spi[kParamUtt + (GRAN ? quad : 0)];
-      const bool use_row = spi[kParamRowFlag + quad * 32 + lane] != 0;   // takes part in the fused FindMinMax
+      const int spi_row_flag = spi[kParamRowFlag + quad * 32 + lane];    // LSM: the row's output row
+      const bool use_row = spi_row_flag != 0;            // takes part in the fused FindMinMax
       float vmin = FLT_MAX, vmax = -FLT_MAX;
 
       tq = prof_on ? clock64() : 0;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       if (prof_on) pr[1] += clock64() - tq;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN + half * C::kPartCols);
 
+      if constexpr (LSM) {
+        // ---- output layer fused with LogSoftmax (src/nnet.cc:137-146 -> ApplyLogSoftMax, src/vector.cc:110-122),
+        //      the prior (src/am.cc:109-112) and the per-frame argmax; 16 columns at a time, the next
+        //      piece's tcgen05.ld in flight while this one is worked on ----
+        const bool stats = p.lsm_softmax != 0 && sub < n_tiles;
+        const int out_row = spi_row_flag;                // where my accumulator row goes; -1: nowhere
+        const float neg_zero = __int_as_float((int)0x80000000 | p.lsm_zero);
+        const int colh = n0 + half * C::kPartCols;       // first column of this warp's part of the tile
+        const int n_piece = min(C::kPartCols / 16, (p.N - colh + 15) >> 4);   // warp-uniform; N % 4 == 0
+        const uint32_t taddr_h = taddr;
+        auto piece = [&](const uint32_t(&raw)[16], const int k) {
+          const int pcol = half * C::kPartCols + k * 16; // column within the tile
+          const int col0 = n0 + pcol;
+          const bool ragged = col0 + 16 > p.N;
+          float2 v2[8];
+          lsm_value<KIND>(raw, sp, corr_off, pcol, rc, flags, neg_zero, v2);
+          if (stats) {
+            lsm_stats(v2, ragged ? p.N - col0 : 16, lsm_m, lsm_s);
+            return;
+          }
+          lsm_finish(v2, sp + kParamPrior + pcol, p.lsm_softmax != 0, lsm_lse, ragged ? p.N - col0 : 16, col0,
+                     lsm_best, lsm_best_i);
+          if (KIND == kKindI8 && p.out_acc && my_row < p.M) {            // the debug dump
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (col0 + j < p.N)
+                p.out_acc[(int64_t)my_row * p.ld_out + col0 + j] = (int32_t)raw[j] + (spi[corr_off + pcol + j] - rc.row_corr);
+            }
+          }
+          if (p.out_f32) {
+            // registers -> swizzled staging tile (32 rows x 16 columns) -> 16-byte row pieces, 8 rows per
+            // warp store: every row goes to its own output row (the compact frame index of its
+            // utterance), or nowhere
+            const int sw = (lane >> 1) & 3;
+            __syncwarp();                                // the previous piece's reads of the tile
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *reinterpret_cast<float4 *>(stg + lane * 64 + ((q ^ sw) << 4)) =
+                  make_float4(v2[2 * q].x, v2[2 * q].y, v2[2 * q + 1].x, v2[2 * q + 1].y);
+            }
+            __syncwarp();
+            const int q = lane & 3;
+            const bool col_ok = col0 + 4 * q < p.N;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2);
+              const int orow = __shfl_sync(0xffffffffu, out_row, r);
+              const float4 val = *reinterpret_cast<const float4 *>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              if (orow >= 0 && col_ok)
+                __stcs(reinterpret_cast<float4 *>(p.out_f32 + (int64_t)orow * p.ld_out + col0 + 4 * q), val);
+            }
+          }
+        };
+        if (!(p.debug & 1)) {
+          uint32_t ra[16], rb[16];
+          if (n_piece > 0) tmem_ld16_issue(taddr_h, ra);
+          for (int k = 0; k < n_piece; k += 2) {
+            tmem_ld16_wait(ra);
+            if (k + 1 < n_piece) tmem_ld16_issue(taddr_h + (uint32_t)((k + 1) * 16), rb);
+            piece(ra, k);
+            if (k + 1 < n_piece) {
+              tmem_ld16_wait(rb);
+              if (k + 2 < n_piece) tmem_ld16_issue(taddr_h + (uint32_t)((k + 2) * 16), ra);
+              piece(rb, k + 1);
+            }
+          }
+        }
+      } else
       for (int c = 0; c < 4; ++c) {
         const int pcol = half * 128 + c * 32;            // column within the tile
         const int col0 = n0 + pcol;
@@ -678,6 +951,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         acc_phase ^= 1;
       }
 
+      if constexpr (LSM) {
+        const float kLog2e = 1.4426950408889634f;
+        const int xr = quad * 32 + lane;
+        if (p.lsm_softmax && sub == n_tiles - 1) {       // end of the first sweep: the row's log-sum-exp
+          xchg_stats[half * kTileM + xr] = make_float2(lsm_m, lsm_s);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * C::kParts) : "memory");   // this row quadrant's warps
+          float mm = -FLT_MAX;
+#pragma unroll
+          for (int h = 0; h < C::kParts; ++h) mm = fmaxf(mm, xchg_stats[h * kTileM + xr].x);
+          float ss = 0.0f;
+#pragma unroll
+          for (int h = 0; h < C::kParts; ++h) {          // column parts in ascending order
+            const float2 o = xchg_stats[h * kTileM + xr];
+            ss += o.y * ex2_approx((o.x - mm) * kLog2e);
+          }
+          lsm_lse = mm + logf(ss);
+          lsm_m = -FLT_MAX;
+          lsm_s = 0.0f;
+        }
+        if (sub == n_subs - 1) {                         // end of the unit: argmax of the finished row
+          const int out_row = spi_row_flag;
+          xchg_best[half * kTileM + xr] = make_float2(lsm_best, __int_as_float(lsm_best_i));
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * C::kParts) : "memory");
+          if (half == 0 && p.lsm_argmax && out_row >= 0) {
+#pragma unroll
+            for (int h = 1; h < C::kParts; ++h) {
+              const float2 o = xchg_best[h * kTileM + xr];
+              const int oi = __float_as_int(o.y);
+              if (o.x > lsm_best || (o.x == lsm_best && oi < lsm_best_i)) {
+                lsm_best = o.x;
+                lsm_best_i = oi;
+              }
+            }
+            p.lsm_argmax[out_row] = lsm_best_i == 0x7fffffff ? 0 : lsm_best_i;
+          }
+          lsm_best = -FLT_MAX;
+          lsm_best_i = 0x7fffffff;
+        }
+      }
+
       if (p.minmax) {
         if (!use_row) {
           vmin = FLT_MAX;
@@ -711,18 +1024,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const int n_gran = (p.M + kRowGran - 1) / kRowGran;
     int pslot = 0;
     uint32_t pphase = 0;
-    for (int tile = group_id; tile < total_tiles; tile += n_groups) {
-      const int m0 = (tile / n_tiles) * kGroupM + (int)rank * kTileM;    // this CTA's 128 rows
-      const int n0 = (tile % n_tiles) * kTileN;
+    for (int unit = group_id; unit < n_units; unit += n_groups)
+    for (int sub = 0; sub < n_subs; ++sub) {
+      const int mt = LSM ? unit : unit / n_tiles;
+      const int nt = LSM ? (sub >= n_tiles ? sub - n_tiles : sub) : unit % n_tiles;
+      const int m0 = mt * kGroupM + (int)rank * kTileM;  // this CTA's 128 rows
+      const int n0 = nt * kTileN;
       mbar_wait(bar_pempty + 8 * pslot, pphase ^ 1);
       float *sp = sp_all + pslot * kParamSlotWords;
       int32_t *spi = reinterpret_cast<int32_t *>(sp);
       // per quadrant (granule mode) or per tile: utterance and its activation quantisation
+      // (the float kinds have no per-utterance arithmetic and no GRAN instantiation, but the fused output
+      //  layer still needs every quadrant's utterance for the row mapping of a packed row space)
+      const bool per_quad = GRAN || (LSM && p.gran != 0);
       int utt_q[4];
       int32_t zp_q[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        utt_q[g] = p.tile_utt ? __ldg(p.tile_utt + min(m0 / kRowGran + (GRAN ? g : 0), n_gran - 1)) : 0;
+        utt_q[g] = p.tile_utt ? __ldg(p.tile_utt + min(m0 / kRowGran + (per_quad ? g : 0), n_gran - 1)) : 0;
         zp_q[g] = 0;
       }
       if (KIND == kKindI8) {
@@ -747,6 +1066,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         sp[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.0f;
         sp[kTileN + c] = p.bn_scale ? __ldg(p.bn_scale + n0 + c) : 1.0f;
         sp[2 * kTileN + c] = p.bn_offset ? __ldg(p.bn_offset + n0 + c) : 0.0f;
+        if (LSM) sp[kParamPrior + c] = (p.lsm_prior && n0 + c < p.N) ? __ldg(p.lsm_prior + n0 + c) : 0.0f;
         const int32_t colsum = (KIND == kKindI8) ? __ldg(p.b_colsum + n0 + c) : 0;
 #pragma unroll
         for (int g = 0; g < (GRAN ? 4 : 1); ++g)
@@ -765,7 +1085,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         }
         spi[kParamRowCorr + 32 * j + lane] = p.zp_b * rsum;
         int flag = 0;
-        if (p.minmax) {
+        if (LSM) {
+          // the output row of this accumulator row: the frame's index in the caller's compact matrix
+          // (or the row itself, lsm_rowspace), -1 for context / padding rows
+          int pos = row, P = p.M;
+          int64_t base = 0;
+          if (p.utts) {
+            const int u = utt_q[per_quad ? j : 0];
+            const UttRows ur = p.utts[u];
+            pos = row - ur.row_off;
+            P = ur.rows;
+            if (p.lsm_out_row_off) base = p.lsm_out_row_off[u];
+          }
+          const bool ok = row < p.M && pos >= p.lsm_left && pos < P - p.lsm_right;
+          flag = !ok ? -1 : p.lsm_rowspace ? row : (int)(base + (pos - p.lsm_left));
+        } else if (p.minmax) {
           int pos = row, P = p.M;
           if (p.utts) {
             const UttRows ur = p.utts[utt_q[GRAN ? j : 0]];
@@ -931,24 +1265,28 @@ int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t 
   return CE_GPU_OK;
 }
 
-template <int KIND, int CG, bool GRAN = false>
+template <int KIND, int CG, bool GRAN = false, bool LSM = false>
 int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, LSM>;
   CUtensorMap ma0, ma1, mb0, mb1, mo0, mo1;
   const bool out_is_bf16 = (KIND == kKindBF16 || KIND == kKindBF16X3) && args.out_bf16 != nullptr;
   const void *o0 = out_is_bf16 ? static_cast<const void *>(args.out_bf16) : static_cast<const void *>(args.out_f32);
-  if (o0 == nullptr) {
+  if (o0 == nullptr && !LSM) {
     SetError("GemmLaunch: no output buffer");
     return CE_GPU_EINVAL;
   }
-  CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M,
-                      (KIND == kKindBF16X3 && out_is_bf16) ? 2 * args.n_store : args.n_store, args.ld_out, &mo0));
-  if (args.out_lo) {
+  CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
+  if (LSM) {
+    mo0 = ma0;                                           // LSM rows leave through plain stores
+  } else {
+    CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M,
+                        (KIND == kKindBF16X3 && out_is_bf16) ? 2 * args.n_store : args.n_store, args.ld_out, &mo0));
+  }
+  if (args.out_lo && !LSM) {
     CE_CHECK(MakeOutMap(false, args.out_lo, args.M, args.n_store, args.ld_out, &mo1));
   } else {
     mo1 = mo0;                                           // never used by the kernel
   }
-  CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
   CE_CHECK(MakeMap(KIND, ops.a[1] ? ops.a[1] : ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma1));
   CE_CHECK(MakeMap(KIND, ops.b[0], ops.rows_b, ops.k_total, C::kBRows, &mb0));
   CE_CHECK(MakeMap(KIND, ops.b[1] ? ops.b[1] : ops.b[0], ops.rows_b, ops.k_total, C::kBRows, &mb1));
@@ -956,7 +1294,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   int dev = 0;
   CE_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !configured[dev]) {
-    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND, CG, GRAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CE_CUDA(cudaFuncSetAttribute(gemm_kernel<KIND, CG, GRAN, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes));
     configured[dev] = true;
   }
@@ -965,11 +1303,11 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   const int n_tiles = (args.N + kTileN - 1) / kTileN;
   const int64_t tiles = (int64_t)m_tiles * n_tiles;
   if (tiles <= 0) return CE_GPU_OK;
-  const int groups = (int)std::min<int64_t>(tiles, SmCount() / CG);
+  const int groups = (int)std::min<int64_t>(LSM ? m_tiles : tiles, SmCount() / CG);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(groups * CG));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -980,7 +1318,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(kProfGemm, s);
-  CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG, GRAN>, ma0, ma1, mb0, mb1, mo0, mo1, args));
+  CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG, GRAN, LSM>, ma0, ma1, mb0, mb1, mo0, mo1, args));
   CE_LAUNCHED();
   return CE_GPU_OK;
 }
@@ -1027,6 +1365,7 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
       if (!on) return;
       unsigned long long h[8];
       if (cudaStreamSynchronize(s) != cudaSuccess || cudaMemcpy(h, buf, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+      constexpr int kEpiWarps = 8;
       const double w = 1965.0 * SmCount() * kEpiWarps;   // cycles -> us per epilogue warp (at the maximum clock)
       fprintf(stderr, "gemm M %d N %d taps %d: epilogue warp us: loop %.1f = wait-params %.1f + wait-accumulator %.1f + "
               "tcgen05.ld %.1f + math %.1f + stage/store %.1f + tail %.1f + rest; %.1f tiles\n", M, N, taps, h[6] / w,
@@ -1036,6 +1375,28 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
   static const int cta_group = getenv("CE_GPU_CTA_GROUP") ? atoi(getenv("CE_GPU_CTA_GROUP")) : 2;
   // granule mode only changes the int8 epilogue (the float kinds carry no per-utterance parameters)
   const bool gran = args.gran != 0 && kind == kKindI8 && args.tile_utt != nullptr;
+  if (args.lsm) {
+    if (args.N % 4 != 0 || (args.out_f32 && (args.ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(args.out_f32) & 15) != 0))) {
+      SetError("GemmLaunch: the fused LogSoftmax output needs N %% 4 == 0 and 16-byte aligned rows (N %d, ld %lld)",
+               args.N, (long long)args.ld_out);
+      return CE_GPU_EINVAL;
+    }
+    if (cta_group == 1) {
+      switch (kind) {
+        case kKindI8: return gran ? LaunchKind<kKindI8, 1, true, true>(ops, args, s) : LaunchKind<kKindI8, 1, false, true>(ops, args, s);
+        case kKindBF16: return LaunchKind<kKindBF16, 1, false, true>(ops, args, s);
+        case kKindTF32: return LaunchKind<kKindTF32, 1, false, true>(ops, args, s);
+        case kKindBF16X3: return LaunchKind<kKindBF16X3, 1, false, true>(ops, args, s);
+      }
+    } else {
+      switch (kind) {
+        case kKindI8: return gran ? LaunchKind<kKindI8, 2, true, true>(ops, args, s) : LaunchKind<kKindI8, 2, false, true>(ops, args, s);
+        case kKindBF16: return LaunchKind<kKindBF16, 2, false, true>(ops, args, s);
+        case kKindTF32: return LaunchKind<kKindTF32, 2, false, true>(ops, args, s);
+        case kKindBF16X3: return LaunchKind<kKindBF16X3, 2, false, true>(ops, args, s);
+      }
+    }
+  }
   if (cta_group == 1) {
     switch (kind) {
       case kKindI8: return gran ? LaunchKind<kKindI8, 1, true>(ops, args, s) : LaunchKind<kKindI8, 1>(ops, args, s);

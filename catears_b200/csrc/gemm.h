@@ -94,6 +94,20 @@ struct GemmArgs {
   int32_t next_tap_off[kMaxTaps];
   int32_t next_lo, next_hi;      // next layer's valid output rows: [next_lo, P - next_hi)
 
+  // ---- LSM: the output layer fused with LogSoftmax + prior + argmax (no logits round trip) ----
+  // One CTA group walks all column tiles of its row tile: a first sweep reduces every row's maximum
+  // and sum of exponentials, a second sweep recomputes the accumulators and writes
+  //   out_f32[out_row][n] = (x[n] - logsumexp(x)) - lsm_prior[n]      src/nnet.cc:137-146, src/am.cc:109-112
+  // for the rows [lsm_left, P - lsm_right) of every utterance block, plus the row's argmax.
+  int32_t lsm;                   // 1 = on (out_f32 / ld_out = destination; may be nullptr: argmax only)
+  int32_t lsm_softmax;           // 0: no LogSoftmax layer (one sweep: prior + argmax only)
+  int32_t lsm_left, lsm_right;
+  int32_t lsm_rowspace;          // 1: out_row = the row itself (a workspace in row space), else compact:
+  const int64_t *lsm_out_row_off;  //  out_row = lsm_out_row_off[utt] + (pos - lsm_left); nullptr = 0
+  const float *lsm_prior;        // [N] log prior; nullptr = none
+  int32_t *lsm_argmax;           // [out rows] first maximum of the finished row; nullptr = off
+  int32_t lsm_zero;              // always 0 (an opaque -0.0 for the kernel's un-fused multiply, see lsm_value)
+
   unsigned long long *dbg;       // CE_GPU_GEMM_PROF: 8 cycle counters of the epilogue warps (gemm.cu), nullptr = off
 };
 

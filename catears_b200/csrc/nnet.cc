@@ -39,7 +39,7 @@ ce_gpu_model::~ce_gpu_model() {
     b.w[0].Free(); b.w[1].Free(); b.bias.Free(); b.bn_scale.Free(); b.bn_offset.Free(); b.colsum.Free();
   }
   for (auto &g : gen) { g.idx.Free(); g.scale.Free(); g.offset.Free(); }
-  log_prior.Free(); cmvn_dev.Free(); out_ids.Free();
+  log_prior.Free(); zero_prior.Free(); cmvn_dev.Free(); out_ids.Free();
   stage_pcm.Free(); stage_feats.Free(); feats.Free(); fbank_chunks.Free(); acc_dump.Free();
   stage_argmax_all.Free();
   ws[0].Free(); ws[1].Free();
@@ -127,6 +127,8 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     std::vector<float> lp(prior.size());
     for (size_t i = 0; i < prior.size(); ++i) lp[i] = logf(prior[i]);
     CE_CHECK(Upload(&m->log_prior, lp.data(), sizeof(float) * lp.size()));
+    std::fill(lp.begin(), lp.end(), 0.0f);               // rows that are already final (fused output layer)
+    CE_CHECK(Upload(&m->zero_prior, lp.data(), sizeof(float) * lp.size()));
   }
 
   const int tile_k = KindTileK(m->kind);
@@ -223,6 +225,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     if (v >= kTileM) m->max_chunk_rows = v;
   }
   if (const char *e = getenv("CE_GPU_OVERLAP")) m->overlap = atoi(e) != 0;
+  if (const char *e = getenv("CE_GPU_FUSED_OUTPUT")) m->fused_output = atoi(e) != 0;   // 0: A/B against the separate kernel
   int prio_lo = 0, prio_hi = 0;
   CE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < 2; ++i) {
@@ -606,6 +609,11 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
 
   m->kept_valid = false;
   m->last_n_utts = n_utts;
+  // Fused output layer (GemmArgs::lsm): every row's arithmetic is the same whatever the output mode, so
+  // dense rows, selected rows, batches and micro-batches stay bit-identical to each other.
+  const bool lsm_dense = m->out_sel.mode == kOutDense;
+  const bool lsm = m->fused_output && NP % 4 == 0 &&
+                   (!lsm_dense || loglik_dev == nullptr || (reinterpret_cast<uintptr_t>(loglik_dev) & 15) == 0);
   HostMark("chunk: first quantize");
   for (int b = 0; b < nb; ++b) {
     const DeviceBlock &D = m->blocks[b];
@@ -701,6 +709,26 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         a.n_store = next_c;
       }
     }
+    if (last && lsm) {
+      // the output layer writes the finished rows itself: LogSoftmax, prior and argmax in its epilogue
+      a.lsm = 1;
+      a.lsm_softmax = m->prog.log_softmax ? 1 : 0;
+      a.lsm_left = L;
+      a.lsm_right = R;
+      a.lsm_prior = m->log_prior.as<float>();
+      a.out_lo = nullptr;
+      a.round_tf32 = 0;
+      if (lsm_dense) {
+        a.out_f32 = loglik_dev;                          // may be nullptr: argmax only
+        a.ld_out = NP;
+        a.lsm_out_row_off = w->outrow_table.dev<int64_t>();
+        a.lsm_argmax = argmax_dev;
+      } else {                                           // finished rows in row space, selected below
+        a.out_f32 = w->logits.as<float>();
+        a.ld_out = ldp;
+        a.lsm_rowspace = 1;
+      }
+    }
     if (s_gemm != s) {
       CE_CUDA(cudaEventRecord(w->to_hi, s));
       CE_CUDA(cudaStreamWaitEvent(s_gemm, w->to_hi, 0));
@@ -722,10 +750,11 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   }
 
   HostMark("chunk: quantize launches");
+  if (lsm && lsm_dense) return CE_GPU_OK;
   CE_CHECK(FinalizeLaunch(w->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
-                          w->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax,
-                          m->log_prior.as<float>(), loglik_dev, m->out_words(), argmax_dev, s,
-                          m->out_sel));
+                          w->outrow_table.dev<int64_t>(), L, R, lsm ? false : m->prog.log_softmax,
+                          lsm ? m->zero_prior.as<float>() : m->log_prior.as<float>(), loglik_dev, m->out_words(),
+                          argmax_dev, s, m->out_sel));
   HostMark("chunk: finalize");
   return CE_GPU_OK;
 }
