@@ -66,7 +66,7 @@ struct Cfg {
   static constexpr int kParts = kEpiWarps / 4;           // column parts of a tile, one epilogue warp each
   static constexpr int kPartCols = kTileN / kParts;
   static constexpr int kStgBytes = LSM ? 32 * 64 : kOutTileBytes;   // staging per epilogue warp
-  static constexpr int kMaxRegs = LSM ? 104 : 128;       // (2 + kEpiWarps + 1) warps x 32 x kMaxRegs <= 64 K
+  static constexpr int kMaxRegs = LSM ? 96 : 128;        // warps (rounded up to 4) x 32 x kMaxRegs <= 64 K registers
   static constexpr int kStages = (CG == 2) ? 5 : 3;
   static constexpr int kBRows = kTileN / CG;             // weight rows staged per CTA
   static constexpr int kBBytes = kBRows * kTileKBytes;
@@ -108,11 +108,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error), never a hung GPU.
+// Bounded waits: a protocol bug becomes a trap (reported as a CUDA error), never a hung GPU.
+// mbar_wait: for the warps whose wake-up latency is on the critical path (MMA issuer, epilogue); the
+// clock is read once per 256 failed tries, so the polling loop is three instructions.
+// mbar_wait_relaxed: for the warps that run ahead by design (TMA producer, parameter prefetcher): the
+// try carries a suspend-time hint, the warp sleeps in hardware instead of taking issue slots from the
+// epilogue warps of its scheduler (ncu: the polling loops were a fifth of the instructions of an
+// epilogue-bound launch).
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(400u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 255u) == 0 && clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_suspend(bar, parity)) {
     if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
@@ -131,6 +156,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// The same with an L2 evict-first policy: a stream of results nobody on this GPU reads again must not
+// push the operands out of L2.
+__device__ __forceinline__ void tma_store_2d_stream(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "l"(pol)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -374,9 +410,10 @@ __device__ __forceinline__ void epi_math(const uint32_t (&raw)[32], float (&v)[3
 // fused output layer (LSM): 16 accumulator columns of one row at a time
 // ---------------------------------------------------------------------------
 // The layer's value in the reference's order of operations (as epi_math), two columns per instruction.
+// (An output layer with ReLU / BatchNorm behind it, or the accumulator dump, takes the un-fused path.)
 template <int KIND>
 __device__ __forceinline__ void lsm_value(const uint32_t (&raw)[16], const float *sp, int corr_off, int pcol,
-                                          const RowConst rc, int flags, float neg_zero, float2 (&v2)[8]) {
+                                          const RowConst rc, float neg_zero, float2 (&v2)[8]) {
   const float2 nz2 = make_float2(neg_zero, neg_zero);
   const float4 *b4 = reinterpret_cast<const float4 *>(sp + pcol);
   const int4 *c4 = reinterpret_cast<const int4 *>(sp + corr_off + pcol);
@@ -402,19 +439,6 @@ __device__ __forceinline__ void lsm_value(const uint32_t (&raw)[16], const float
     }
     v2[2 * q] = add2(x0, make_float2(bb.x, bb.y));                       // nnet.cc:34
     v2[2 * q + 1] = add2(x1, make_float2(bb.z, bb.w));
-  }
-  if (flags & 3) {                                       // an output layer with ReLU / BatchNorm behind it
-    const float *bs = sp + kTileN + pcol, *bo = sp + 2 * kTileN + pcol;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float x[2] = {v2[j].x, v2[j].y};
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (flags & 1) asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(x[e]) : "f"(x[e]));   // nnet.cc:156
-        if (flags & 2) x[e] = __fadd_rn(__fmul_rn(x[e], bs[2 * j + e]), bo[2 * j + e]);    // nnet.cc:114-115
-      }
-      v2[j] = make_float2(x[0], x[1]);
-    }
   }
 }
 
@@ -747,68 +771,87 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         // ---- output layer fused with LogSoftmax (src/nnet.cc:137-146 -> ApplyLogSoftMax, src/vector.cc:110-122),
         //      the prior (src/am.cc:109-112) and the per-frame argmax; 16 columns at a time, the next
         //      piece's tcgen05.ld in flight while this one is worked on ----
+        constexpr int kPieces = C::kPartCols / 16;
         const bool stats = p.lsm_softmax != 0 && sub < n_tiles;
         const int out_row = spi_row_flag;                // where my accumulator row goes; -1: nowhere
         const float neg_zero = __int_as_float((int)0x80000000 | p.lsm_zero);
         const int colh = n0 + half * C::kPartCols;       // first column of this warp's part of the tile
-        const int n_piece = min(C::kPartCols / 16, (p.N - colh + 15) >> 4);   // warp-uniform; N % 4 == 0
-        const uint32_t taddr_h = taddr;
+        const int n_piece = min(kPieces, (p.N - colh + 15) >> 4);   // warp-uniform; N % 4 == 0
+        // all 32 rows of this warp go to consecutive output rows (blocks never share a 32-row granule):
+        // the staged pieces leave as TMA stores
+        const bool full = __all_sync(0xffffffffu, out_row >= 0) && !(p.debug & 32);
+        const int out_row0 = __shfl_sync(0xffffffffu, out_row, 0);
+        float4 *const out4 = (p.debug & 8) ? nullptr : reinterpret_cast<float4 *>(p.out_f32);   // 8: timing probe
+        const unsigned char *const stg_rd = stg + (lane >> 2) * 64 + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+        unsigned char *const stg_wr = stg + lane * 64;
+        const int sw = (lane >> 1) & 3;
         auto piece = [&](const uint32_t(&raw)[16], const int k) {
           const int pcol = half * C::kPartCols + k * 16; // column within the tile
           const int col0 = n0 + pcol;
-          const bool ragged = col0 + 16 > p.N;
+          const int n_ok = min(16, p.N - col0);          // < 16: the last piece of a ragged row
           float2 v2[8];
-          lsm_value<KIND>(raw, sp, corr_off, pcol, rc, flags, neg_zero, v2);
+          lsm_value<KIND>(raw, sp, corr_off, pcol, rc, neg_zero, v2);
           if (stats) {
-            lsm_stats(v2, ragged ? p.N - col0 : 16, lsm_m, lsm_s);
+            if (!(p.debug & 16)) lsm_stats(v2, n_ok, lsm_m, lsm_s);
+            else lsm_s += v2[0].x;
             return;
           }
-          lsm_finish(v2, sp + kParamPrior + pcol, p.lsm_softmax != 0, lsm_lse, ragged ? p.N - col0 : 16, col0,
-                     lsm_best, lsm_best_i);
-          if (KIND == kKindI8 && p.out_acc && my_row < p.M) {            // the debug dump
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (col0 + j < p.N)
-                p.out_acc[(int64_t)my_row * p.ld_out + col0 + j] = (int32_t)raw[j] + (spi[corr_off + pcol + j] - rc.row_corr);
-            }
-          }
-          if (p.out_f32) {
+          lsm_finish(v2, sp + kParamPrior + pcol, p.lsm_softmax != 0, lsm_lse, n_ok, col0, lsm_best, lsm_best_i);
+          if (out4) {
             // registers -> swizzled staging tile (32 rows x 16 columns) -> 16-byte row pieces, 8 rows per
             // warp store: every row goes to its own output row (the compact frame index of its
             // utterance), or nowhere
-            const int sw = (lane >> 1) & 3;
-            __syncwarp();                                // the previous piece's reads of the tile
+            if (lane == 0) tma_store_wait_read();        // the previous piece's store has read the tile
+            __syncwarp();                                // ... and so have the plain stores' reads
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              *reinterpret_cast<float4 *>(stg + lane * 64 + ((q ^ sw) << 4)) =
+              *reinterpret_cast<float4 *>(stg_wr + ((q ^ sw) << 4)) =
                   make_float4(v2[2 * q].x, v2[2 * q].y, v2[2 * q + 1].x, v2[2 * q + 1].y);
             }
-            __syncwarp();
-            const int q = lane & 3;
-            const bool col_ok = col0 + 4 * q < p.N;
+            if (full) {                                  // warp-uniform
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) tma_store_2d_stream(&map_o0, stg_u32, col0, out_row0);   // columns >= N are clipped
+            } else {
+              __syncwarp();
+              // (the first and the last group of an utterance's block: rows 8 i + lane / 4 of the tile,
+              //  16-byte piece lane % 4, each to its own output row or nowhere)
+              const bool col_ok = 4 * (lane & 3) < n_ok;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = 8 * i + (lane >> 2);
-              const int orow = __shfl_sync(0xffffffffu, out_row, r);
-              const float4 val = *reinterpret_cast<const float4 *>(stg + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
-              if (orow >= 0 && col_ok)
-                __stcs(reinterpret_cast<float4 *>(p.out_f32 + (int64_t)orow * p.ld_out + col0 + 4 * q), val);
+              for (int i = 0; i < 4; ++i) {
+                const int orow = __shfl_sync(0xffffffffu, out_row, 8 * i + (lane >> 2));
+                const float4 val = *reinterpret_cast<const float4 *>(stg_rd + i * 512);
+                if (orow >= 0 && col_ok)
+                  __stcs(reinterpret_cast<float4 *>(p.out_f32 + (int64_t)orow * p.ld_out + col0) + (lane & 3), val);
+              }
             }
           }
         };
         if (!(p.debug & 1)) {
-          uint32_t ra[16], rb[16];
-          if (n_piece > 0) tmem_ld16_issue(taddr_h, ra);
-          for (int k = 0; k < n_piece; k += 2) {
-            tmem_ld16_wait(ra);
-            if (k + 1 < n_piece) tmem_ld16_issue(taddr_h + (uint32_t)((k + 1) * 16), rb);
-            piece(ra, k);
-            if (k + 1 < n_piece) {
-              tmem_ld16_wait(rb);
-              if (k + 2 < n_piece) tmem_ld16_issue(taddr_h + (uint32_t)((k + 2) * 16), ra);
-              piece(rb, k + 1);
+#ifdef CE_LSM_PIPELINED_LD
+          uint32_t r[2][16];
+          if (n_piece > 0) tmem_ld16_issue(taddr, r[0]);
+#pragma unroll
+          for (int k = 0; k < kPieces; ++k) {
+            if (k < n_piece) {
+              tmem_ld16_wait(r[k & 1]);
+              if (k + 1 < kPieces && k + 1 < n_piece) tmem_ld16_issue(taddr + (uint32_t)((k + 1) * 16), r[(k + 1) & 1]);
+              piece(r[k & 1], k);
             }
           }
+#else
+          // (one piece in flight per warp: with four warps per scheduler the other warps cover the
+          //  tcgen05.ld, and a second buffer costs 16 of the 96 registers)
+#pragma unroll
+          for (int k = 0; k < kPieces; ++k) {
+            if (k < n_piece) {
+              uint32_t r[16];
+              tmem_ld16_issue(taddr + (uint32_t)(k * 16), r);
+              tmem_ld16_wait(r);
+              piece(r, k);
+            }
+          }
+#endif
         }
       } else
       for (int c = 0; c < 4; ++c) {
@@ -1021,103 +1064,131 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     // One tile ahead of the epilogue: everything its warps need per tile -- per-column bias /
     // batch-norm / integer-correction arrays, per-row corrections and FindMinMax flags, per-quadrant
     // scale and utterance -- goes into one of two shared-memory slots, signalled by an mbarrier.
+    // Everything is LOADED (into registers) before the wait for a free slot, so the global-memory latency
+    // of a tile's parameters overlaps the epilogue of the tile before; the per-row and per-utterance
+    // values of the fused output layer are the same for all column tiles of a unit and are fetched once.
     const int n_gran = (p.M + kRowGran - 1) / kRowGran;
     int pslot = 0;
     uint32_t pphase = 0;
+    const bool per_quad = GRAN || (LSM && p.gran != 0);  // (the float kinds have no per-utterance arithmetic and
+    // no GRAN instantiation, but the fused output layer still needs every quadrant's utterance for the
+    // row mapping of a packed row space)
+    int utt_q[4] = {0, 0, 0, 0};
+    int32_t zp_q[4] = {0, 0, 0, 0};
+    float scale_q[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    int32_t row_corr[4] = {0, 0, 0, 0}, row_flag[4] = {0, 0, 0, 0};
     for (int unit = group_id; unit < n_units; unit += n_groups)
     for (int sub = 0; sub < n_subs; ++sub) {
       const int mt = LSM ? unit : unit / n_tiles;
       const int nt = LSM ? (sub >= n_tiles ? sub - n_tiles : sub) : unit % n_tiles;
       const int m0 = mt * kGroupM + (int)rank * kTileM;  // this CTA's 128 rows
       const int n0 = nt * kTileN;
-      mbar_wait(bar_pempty + 8 * pslot, pphase ^ 1);
-      float *sp = sp_all + pslot * kParamSlotWords;
-      int32_t *spi = reinterpret_cast<int32_t *>(sp);
-      // per quadrant (granule mode) or per tile: utterance and its activation quantisation
-      // (the float kinds have no per-utterance arithmetic and no GRAN instantiation, but the fused output
-      //  layer still needs every quadrant's utterance for the row mapping of a packed row space)
-      const bool per_quad = GRAN || (LSM && p.gran != 0);
-      int utt_q[4];
-      int32_t zp_q[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        utt_q[g] = p.tile_utt ? __ldg(p.tile_utt + min(m0 / kRowGran + (per_quad ? g : 0), n_gran - 1)) : 0;
-        zp_q[g] = 0;
-      }
-      if (KIND == kKindI8) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (!GRAN && g > 0) {
-            zp_q[g] = zp_q[0];
-            continue;
-          }
-          const QParam q = p.qa[utt_q[g]];
-          zp_q[g] = q.zero_point;
-          if (lane == g) sp[kParamScale + g] = __fmul_rn(q.scale, p.scale_b);   // matrix.cc:403 (float * float)
-        }
-      } else if (lane < 4) {
-        sp[kParamScale + lane] = 1.0f;
-      }
-      if (lane < 4) spi[kParamUtt + lane] = utt_q[lane];
       // per column: 8 columns a lane (parameter arrays are padded to kTileN)
+      float c_bias[kTileN / 32], c_bns[kTileN / 32], c_bno[kTileN / 32], c_prior[kTileN / 32];
+      int32_t c_sum[kTileN / 32];
 #pragma unroll
       for (int j = 0; j < kTileN / 32; ++j) {
         const int c = lane + 32 * j;
-        sp[c] = p.bias ? __ldg(p.bias + n0 + c) : 0.0f;
-        sp[kTileN + c] = p.bn_scale ? __ldg(p.bn_scale + n0 + c) : 1.0f;
-        sp[2 * kTileN + c] = p.bn_offset ? __ldg(p.bn_offset + n0 + c) : 0.0f;
-        if (LSM) sp[kParamPrior + c] = (p.lsm_prior && n0 + c < p.N) ? __ldg(p.lsm_prior + n0 + c) : 0.0f;
-        const int32_t colsum = (KIND == kKindI8) ? __ldg(p.b_colsum + n0 + c) : 0;
-#pragma unroll
-        for (int g = 0; g < (GRAN ? 4 : 1); ++g)
-          spi[(3 + g) * kTileN + c] = (KIND == kKindI8) ? p.k_true * zp_q[g] * p.zp_b - zp_q[g] * colsum : 0;
+        c_bias[j] = p.bias ? __ldg(p.bias + n0 + c) : 0.0f;
+        c_bns[j] = p.bn_scale ? __ldg(p.bn_scale + n0 + c) : 1.0f;
+        c_bno[j] = p.bn_offset ? __ldg(p.bn_offset + n0 + c) : 0.0f;
+        c_prior[j] = (LSM && p.lsm_prior && n0 + c < p.N) ? __ldg(p.lsm_prior + n0 + c) : 0.0f;
+        c_sum[j] = (KIND == kKindI8) ? __ldg(p.b_colsum + n0 + c) : 0;
       }
-      // per row: 4 rows a lane, row group j = accumulator quadrant j
+      if (!LSM || sub == 0) {
+        // per quadrant (granule mode) or per tile: utterance and its activation quantisation
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = m0 + 32 * j + lane;
-        int32_t rsum = 0;
+        for (int g = 0; g < 4; ++g) {
+          utt_q[g] = p.tile_utt ? __ldg(p.tile_utt + min(m0 / kRowGran + (per_quad ? g : 0), n_gran - 1)) : 0;
+          zp_q[g] = 0;
+        }
         if (KIND == kKindI8) {
-          for (int t = 0; t < p.n_taps; ++t) {
-            const int r = row + p.tap_off[t];
-            if (r >= 0 && r < p.M) rsum += __ldg(p.a_rowsum + r);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (!GRAN && g > 0) {
+              zp_q[g] = zp_q[0];
+              scale_q[g] = scale_q[0];
+              continue;
+            }
+            const QParam q = p.qa[utt_q[g]];
+            zp_q[g] = q.zero_point;
+            scale_q[g] = __fmul_rn(q.scale, p.scale_b);                 // matrix.cc:403 (float * float)
           }
         }
-        spi[kParamRowCorr + 32 * j + lane] = p.zp_b * rsum;
-        int flag = 0;
-        if (LSM) {
-          // the output row of this accumulator row: the frame's index in the caller's compact matrix
-          // (or the row itself, lsm_rowspace), -1 for context / padding rows
-          int pos = row, P = p.M;
-          int64_t base = 0;
-          if (p.utts) {
-            const int u = utt_q[per_quad ? j : 0];
-            const UttRows ur = p.utts[u];
-            pos = row - ur.row_off;
-            P = ur.rows;
-            if (p.lsm_out_row_off) base = p.lsm_out_row_off[u];
+        // per row: 4 rows a lane, row group j = accumulator quadrant j
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = m0 + 32 * j + lane;
+          int32_t rsum = 0;
+          if (KIND == kKindI8) {
+            for (int t = 0; t < p.n_taps; ++t) {
+              const int r = row + p.tap_off[t];
+              if (r >= 0 && r < p.M) rsum += __ldg(p.a_rowsum + r);
+            }
           }
-          const bool ok = row < p.M && pos >= p.lsm_left && pos < P - p.lsm_right;
-          flag = !ok ? -1 : p.lsm_rowspace ? row : (int)(base + (pos - p.lsm_left));
-        } else if (p.minmax) {
-          int pos = row, P = p.M;
-          if (p.utts) {
-            const UttRows ur = p.utts[utt_q[GRAN ? j : 0]];
-            pos = row - ur.row_off;
-            P = ur.rows;
-          }
-          if (pos >= p.mm_lo && pos < P - p.mm_hi) {
-            if (p.next_n_taps == 0) {
-              flag = 1;
-            } else {
-              for (int t = 0; t < p.next_n_taps; ++t) {
-                const int o = pos - p.next_tap_off[t];
-                if (o >= p.next_lo && o < P - p.next_hi) flag = 1;
+          row_corr[j] = p.zp_b * rsum;
+          int flag = 0;
+          if (LSM) {
+            // the output row of this accumulator row: the frame's index in the caller's compact matrix
+            // (or the row itself, lsm_rowspace), -1 for context / padding rows
+            int pos = row, P = p.M;
+            int64_t base = 0;
+            if (p.utts) {
+              const int u = utt_q[per_quad ? j : 0];
+              const UttRows ur = p.utts[u];
+              pos = row - ur.row_off;
+              P = ur.rows;
+              if (p.lsm_out_row_off) base = p.lsm_out_row_off[u];
+            }
+            const bool ok = row < p.M && pos >= p.lsm_left && pos < P - p.lsm_right;
+            flag = !ok ? -1 : p.lsm_rowspace ? row : (int)(base + (pos - p.lsm_left));
+          } else if (p.minmax) {
+            int pos = row, P = p.M;
+            if (p.utts) {
+              const UttRows ur = p.utts[utt_q[GRAN ? j : 0]];
+              pos = row - ur.row_off;
+              P = ur.rows;
+            }
+            if (pos >= p.mm_lo && pos < P - p.mm_hi) {
+              if (p.next_n_taps == 0) {
+                flag = 1;
+              } else {
+                for (int t = 0; t < p.next_n_taps; ++t) {
+                  const int o = pos - p.next_tap_off[t];
+                  if (o >= p.next_lo && o < P - p.next_hi) flag = 1;
+                }
               }
             }
           }
+          row_flag[j] = flag;
         }
-        spi[kParamRowFlag + 32 * j + lane] = flag;
+      }
+
+      mbar_wait_relaxed(bar_pempty + 8 * pslot, pphase ^ 1);
+      float *sp = sp_all + pslot * kParamSlotWords;
+      int32_t *spi = reinterpret_cast<int32_t *>(sp);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (lane == g) {
+          sp[kParamScale + g] = scale_q[g];
+          spi[kParamUtt + g] = utt_q[g];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kTileN / 32; ++j) {
+        const int c = lane + 32 * j;
+        sp[c] = c_bias[j];
+        sp[kTileN + c] = c_bns[j];
+        sp[2 * kTileN + c] = c_bno[j];
+        if (LSM) sp[kParamPrior + c] = c_prior[j];
+#pragma unroll
+        for (int g = 0; g < (GRAN ? 4 : 1); ++g)
+          spi[(3 + g) * kTileN + c] = (KIND == kKindI8) ? p.k_true * zp_q[g] * p.zp_b - zp_q[g] * c_sum[j] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        spi[kParamRowCorr + 32 * j + lane] = row_corr[j];
+        spi[kParamRowFlag + 32 * j + lane] = row_flag[j];
       }
       __syncwarp();                                      // every lane's stores before the arrive (release)
       if (lane == 0) mbar_arrive(bar_pfull + 8 * pslot);
@@ -1236,9 +1307,10 @@ int MakeMap(int kind, const void *base, int64_t rows, int64_t cols, int box_rows
 }
 
 // 2-D map for the TMA stores of the epilogue: [rows x cols] window of a row-major matrix with row
-// stride ld (elements), box = 32 rows x 128 bytes, 128B swizzle.
-int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap *map) {
-  const MapKey mk = {base, rows, cols, ld, 32, 16 + (bf16 ? 1 : 0)};
+// stride ld (elements), box = 32 rows x 128 bytes, 128B swizzle (box64: 32 rows x 64 bytes, 64B swizzle).
+int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t ld, CUtensorMap *map,
+               bool box64 = false) {
+  const MapKey mk = {base, rows, cols, ld, 32, 16 + (bf16 ? 1 : 0) + (box64 ? 2 : 0)};
   if (Maps().Find(mk, map)) return CE_GPU_OK;
   EncodeTiledFn fn;
   CE_CHECK(GetEncodeFn(&fn));
@@ -1250,11 +1322,11 @@ int MakeOutMap(bool bf16, const void *base, int64_t rows, int64_t cols, int64_t 
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)(ld * elt)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / elt), 32};
+  cuuint32_t box[2] = {(cuuint32_t)((box64 ? 64 : 128) / elt), 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  box64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     SetError("cuTensorMapEncodeTiled (output) failed with CUresult %d (rows %lld cols %lld ld %lld)",
@@ -1277,7 +1349,10 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   }
   CE_CHECK(MakeMap(KIND, ops.a[0], ops.rows_a, args.c_pad, kTileM, &ma0));
   if (LSM) {
-    mo0 = ma0;                                           // LSM rows leave through plain stores
+    // whole 32-row groups of finished rows leave through TMA stores of 32 x 16 columns, the others
+    // through plain stores
+    if (args.out_f32) CE_CHECK(MakeOutMap(false, args.out_f32, args.lsm_out_rows, args.N, args.ld_out, &mo0, true));
+    else mo0 = ma0;
   } else {
     CE_CHECK(MakeOutMap(out_is_bf16, o0, args.M,
                         (KIND == kKindBF16X3 && out_is_bf16) ? 2 * args.n_store : args.n_store, args.ld_out, &mo0));
@@ -1376,6 +1451,10 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
   // granule mode only changes the int8 epilogue (the float kinds carry no per-utterance parameters)
   const bool gran = args.gran != 0 && kind == kKindI8 && args.tile_utt != nullptr;
   if (args.lsm) {
+    if (args.relu || args.bn_scale || args.out_acc) {
+      SetError("GemmLaunch: the fused LogSoftmax output takes a plain Linear layer (no ReLU / BatchNorm / accumulator dump)");
+      return CE_GPU_EINVAL;
+    }
     if (args.N % 4 != 0 || (args.out_f32 && (args.ld_out % 4 != 0 || (reinterpret_cast<uintptr_t>(args.out_f32) & 15) != 0))) {
       SetError("GemmLaunch: the fused LogSoftmax output needs N %% 4 == 0 and 16-byte aligned rows (N %d, ld %lld)",
                args.N, (long long)args.ld_out);

@@ -84,7 +84,9 @@ struct GemmArgs {
   int32_t round_tf32;            // out_f32 = tf32-rounded value (so that out_lo is exact)
   int32_t debug;                 // CE_GPU_GEMM_DEBUG bits (timing probes only, results are WRONG):
                                  // 1 = epilogue drains TMEM but skips math and stores,
-                                 // 2 = no tcgen05.mma is issued, 4 = no TMA loads are issued
+                                 // 2 = no tcgen05.mma is issued, 4 = no TMA loads are issued,
+                                 // 8 = fused output layer without its stores, 16 = without its exponentials,
+                                 // 32 = (not a probe: results stay right) plain stores instead of TMA stores
 
   // fused FindMinMax (src/matrix.cc:329-345) for the next layer's Quantize: only rows the next
   // layer's Splice+Narrow actually reads take part.
@@ -104,6 +106,7 @@ struct GemmArgs {
   int32_t lsm_left, lsm_right;
   int32_t lsm_rowspace;          // 1: out_row = the row itself (a workspace in row space), else compact:
   const int64_t *lsm_out_row_off;  //  out_row = lsm_out_row_off[utt] + (pos - lsm_left); nullptr = 0
+  int64_t lsm_out_rows;          // rows of the destination matrix (the bound of the TMA stores)
   const float *lsm_prior;        // [N] log prior; nullptr = none
   int32_t *lsm_argmax;           // [out rows] first maximum of the finished row; nullptr = off
   int32_t lsm_zero;              // always 0 (an opaque -0.0 for the kernel's un-fused multiply, see lsm_value)

@@ -612,7 +612,8 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   // Fused output layer (GemmArgs::lsm): every row's arithmetic is the same whatever the output mode, so
   // dense rows, selected rows, batches and micro-batches stay bit-identical to each other.
   const bool lsm_dense = m->out_sel.mode == kOutDense;
-  const bool lsm = m->fused_output && NP % 4 == 0 &&
+  const DeviceBlock &Dl = m->blocks[nb - 1];
+  const bool lsm = m->fused_output && NP % 4 == 0 && !Dl.meta.relu && Dl.meta.batchnorm < 0 && m->keep_acc != nb - 1 &&
                    (!lsm_dense || loglik_dev == nullptr || (reinterpret_cast<uintptr_t>(loglik_dev) & 15) == 0);
   HostMark("chunk: first quantize");
   for (int b = 0; b < nb; ++b) {
@@ -721,12 +722,14 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
       if (lsm_dense) {
         a.out_f32 = loglik_dev;                          // may be nullptr: argmax only
         a.ld_out = NP;
-        a.lsm_out_row_off = w->outrow_table.dev<int64_t>();
+        a.lsm_out_row_off = w->outrow_table.dev<int64_t>();     // absolute frame index over the batch
+        a.lsm_out_rows = out_off[n_utts];
         a.lsm_argmax = argmax_dev;
       } else {                                           // finished rows in row space, selected below
         a.out_f32 = w->logits.as<float>();
         a.ld_out = ldp;
         a.lsm_rowspace = 1;
+        a.lsm_out_rows = M;
       }
     }
     if (s_gemm != s) {
