@@ -530,6 +530,10 @@ def run_gpu(args):
         "share_of_step": round(gemm_ms / ms_serial, 4),
         "timing": "CUDA events around every launch in a second pass of the same steps "
                   "(%.3f ms/step with the events in)" % (ms_serial / args.steps),
+        "note": "the last launch of every pass is the output layer fused with LogSoftmax + prior + argmax: it "
+                "multiplies its tiles twice (row statistics, then the finished rows) and its time contains what "
+                "the separate log-softmax kernel used to take (kernel_ms_per_step.finalize = 0); `achieved` "
+                "counts the algorithmic FLOPs once",
     }
     fb_gbs = frames * FBANK_BYTES_PER_FRAME * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else 0.0
     roofline_fbank = {"kernel": "fbank_kernel", "bound": "hbm", "achieved": round(fb_gbs, 1),

@@ -329,7 +329,6 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x: MUFU.EX2, tiny 
   }
 CE_F32X2_OP(add2, "add.rn.f32x2")
 CE_F32X2_OP(sub2, "sub.rn.f32x2")
-CE_F32X2_OP(mul2, "mul.rn.f32x2")
 #undef CE_F32X2_OP
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   float2 r;

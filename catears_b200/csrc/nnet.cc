@@ -225,7 +225,7 @@ int ModelBuild(const HostNnet &nn, const std::vector<float> &prior,
     if (v >= kTileM) m->max_chunk_rows = v;
   }
   if (const char *e = getenv("CE_GPU_OVERLAP")) m->overlap = atoi(e) != 0;
-  if (const char *e = getenv("CE_GPU_FUSED_OUTPUT")) m->fused_output = atoi(e) != 0;   // 0: A/B against the separate kernel
+  if (const char *e = getenv("CE_GPU_FUSED_OUTPUT")) m->fused_output = atoi(e);   // 0: A/B against the separate kernel
   int prio_lo = 0, prio_hi = 0;
   CE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int i = 0; i < 2; ++i) {
@@ -613,7 +613,10 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   // dense rows, selected rows, batches and micro-batches stay bit-identical to each other.
   const bool lsm_dense = m->out_sel.mode == kOutDense;
   const DeviceBlock &Dl = m->blocks[nb - 1];
-  const bool lsm = m->fused_output && NP % 4 == 0 && !Dl.meta.relu && Dl.meta.batchnorm < 0 && m->keep_acc != nb - 1 &&
+  // int8 only: its output layer is epilogue-bound either way.  The float kinds' is bound by the multiplications,
+  // and multiplying twice costs them more than the log-softmax kernel did (fp32 = 3 x TF32: 64 k -> 50 k x real
+  // time, bf16x3 125 k -> 107 k, measured) -- they keep the separate kernel (CE_GPU_FUSED_OUTPUT=2 forces it on).
+  const bool lsm = (m->kind == kKindI8 ? m->fused_output != 0 : m->fused_output == 2) && NP % 4 == 0 && !Dl.meta.relu && Dl.meta.batchnorm < 0 && m->keep_acc != nb - 1 &&
                    (!lsm_dense || loglik_dev == nullptr || (reinterpret_cast<uintptr_t>(loglik_dev) & 15) == 0);
   HostMark("chunk: first quantize");
   for (int b = 0; b < nb; ++b) {

@@ -42,7 +42,8 @@ struct ce_gpu_model {
   std::vector<ce::GenStepDev> gen;     // general program only: one entry per Program::steps entry
   ce::DevBuf log_prior;      // log(prior), src/am.cc:43-44
   ce::DevBuf zero_prior;     // zeros of the same length
-  bool fused_output = true;  // LogSoftmax + prior + argmax in the output layer's epilogue (CE_GPU_FUSED_OUTPUT=0: off)
+  int fused_output = 1;      // LogSoftmax + prior + argmax in the output layer's epilogue: 1 = int8 models,
+                             // 0 = never, 2 = every precision (CE_GPU_FUSED_OUTPUT)
   bool has_cmvn = false;
   std::vector<float> cmvn_host;   // num_mel sums + count
   ce::DevBuf cmvn_dev;

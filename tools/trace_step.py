@@ -59,6 +59,17 @@ def main():
     for c, iv in by.items():
         print("  %-9s n=%4d sum %.3f ms union %.3f ms" % (c, len(iv), sum(b - a for a, b in iv), union(iv)))
     print("  union of everything %.3f ms" % union([(a, b) for _, a, b in tr]))
+    # where the GPU idles inside the call: the largest gaps between consecutive kernels
+    ev = sorted(tr, key=lambda t: t[1])
+    gaps, end = [], ev[0][2]
+    print("  first kernel starts at %.3f ms, last ends at %.3f ms" % (ev[0][1], t_end))
+    for i in range(1, len(ev)):
+        if ev[i][1] > end:
+            gaps.append((ev[i][1] - end, i))
+        end = max(end, ev[i][2])
+    print("  idle inside the span: %.3f ms in %d gaps; largest:" % (sum(g for g, _ in gaps), len(gaps)))
+    for g, i in sorted(gaps, reverse=True)[:10]:
+        print("    %.1f us before record %d (%s at %.3f ms, after %s)" % (1e3 * g, i, ev[i][0], ev[i][1], ev[i - 1][0]))
     if len(sys.argv) > 2:
         for c, a, b in tr[:int(sys.argv[2])]:
             print("    %-9s %9.3f -> %9.3f  (%.1f us)" % (c, a, b, 1e3 * (b - a)))
