@@ -623,7 +623,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
   // exponentials, a second one that recomputes the accumulators and writes the finished rows -- so the
   // logits never exist in memory.
   const int n_units = LSM ? m_tiles : total_tiles;
-  const int n_subs = LSM ? (p.lsm_softmax ? 2 * n_tiles : n_tiles) : 1;
+  const int n_subs = LSM ? ((p.lsm_softmax && !p.lsm_single) ? 2 * n_tiles : n_tiles) : 1;
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own operand slices) ===============
@@ -861,7 +861,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
         //      the prior (src/am.cc:109-112) and the per-frame argmax; 16 columns at a time, the next
         //      piece's tcgen05.ld in flight while this one is worked on ----
         constexpr int kPieces = C::kPartCols / 16;
-        const bool stats = p.lsm_softmax != 0 && sub < n_tiles;
+        const bool single = p.lsm_single != 0;           // one sweep: plain result + the row's log-sum-exp
+        const bool stats = p.lsm_softmax != 0 && !single && sub < n_tiles;
         const int out_row = spi_row_flag;                // where my accumulator row goes; -1: nowhere
         const float neg_zero = __int_as_float((int)0x80000000 | p.lsm_zero);
         const int colh = n0 + half * C::kPartCols;       // first column of this warp's part of the tile
@@ -885,7 +886,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             else lsm_s += v2[0].x;
             return;
           }
-          lsm_finish(v2, sp + kParamPrior + pcol, p.lsm_softmax != 0, lsm_lse, n_ok, col0, lsm_best, lsm_best_i);
+          if (single) {
+            float2 t2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t2[j] = v2[j];
+            lsm_stats(t2, n_ok, lsm_m, lsm_s);
+          } else {
+            lsm_finish(v2, sp + kParamPrior + pcol, p.lsm_softmax != 0, lsm_lse, n_ok, col0, lsm_best, lsm_best_i);
+          }
           if (out4) {
             // registers -> swizzled staging tile (32 rows x 16 columns) -> 16-byte row pieces, 8 rows per
             // warp store: every row goes to its own output row (the compact frame index of its
@@ -1086,7 +1094,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
       if constexpr (LSM) {
         const float kLog2e = 1.4426950408889634f;
         const int xr = quad * 32 + lane;
-        if (p.lsm_softmax && sub == n_tiles - 1) {       // end of the first sweep: the row's log-sum-exp
+        if (p.lsm_softmax && sub == n_tiles - 1) {       // end of the first (or only) sweep: the row's log-sum-exp
           xchg_stats[half * kTileM + xr] = make_float2(lsm_m, lsm_s);
           asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * C::kParts) : "memory");   // this row quadrant's warps
           float mm = -FLT_MAX;
@@ -1101,6 +1109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           lsm_lse = mm + logf(ss);
           lsm_m = -FLT_MAX;
           lsm_s = 0.0f;
+          if (p.lsm_single && half == 0 && spi_row_flag >= 0) p.lsm_lse_out[spi_row_flag] = lsm_lse;
         }
         if (sub == n_subs - 1) {                         // end of the unit: argmax of the finished row
           const int out_row = spi_row_flag;

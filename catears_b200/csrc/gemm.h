@@ -109,6 +109,9 @@ struct GemmArgs {
   int64_t lsm_out_rows;          // rows of the destination matrix (the bound of the TMA stores)
   const float *lsm_prior;        // [N] log prior; nullptr = none
   int32_t *lsm_argmax;           // [out rows] first maximum of the finished row; nullptr = off
+  int32_t lsm_single;            // 1: ONE sweep that writes the layer's plain result (row space) and the row's
+  float *lsm_lse_out;            //    log-sum-exp to lsm_lse_out[row] -- for the selecting output kernels, which
+                                 //    then subtract the very number the dense fused output subtracts
   int32_t lsm_zero;              // always 0 (an opaque -0.0 for the kernel's un-fused multiply, see lsm_value)
 
   unsigned long long *dbg;       // CE_GPU_GEMM_PROF: 8 cycle counters of the epilogue warps (gemm.cu), nullptr = off

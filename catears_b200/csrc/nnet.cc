@@ -20,7 +20,7 @@
 void ce_gpu_model::ChunkWs::Free() {
   x0.Free(); feats.Free(); fbank_chunks.Free();
   for (int i = 0; i < 2; ++i) { act_f32[i].Free(); act_lo[i].Free(); act_bf16[i].Free(); }
-  act_u8.Free(); rowsum.Free(); logits.Free(); minmax.Free(); qparams.Free();
+  act_u8.Free(); rowsum.Free(); logits.Free(); row_lse.Free(); minmax.Free(); qparams.Free();
   stage_loglik.Free();
   cmvn_utts.Free(); utt_table.Free(); tile_table.Free(); outrow_table.Free();
   if (stream) cudaStreamDestroy(stream);
@@ -565,6 +565,7 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   const int ldp = RoundUp(NP, 4);
   CE_CHECK(w->x0.Reserve(sizeof(float) * (size_t)M * F));
   CE_CHECK(w->logits.Reserve(sizeof(float) * (size_t)M * ldp));
+  CE_CHECK(w->row_lse.Reserve(sizeof(float) * (size_t)M));
   if (m->kind == kKindI8) {
     CE_CHECK(w->act_f32[0].Reserve(sizeof(float) * (size_t)M * wmax));
     CE_CHECK(w->act_u8.Reserve((size_t)M * wmax));
@@ -616,7 +617,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   // int8 only: its output layer is epilogue-bound either way.  The float kinds' is bound by the multiplications,
   // and multiplying twice costs them more than the log-softmax kernel did (fp32 = 3 x TF32: 64 k -> 50 k x real
   // time, bf16x3 125 k -> 107 k, measured) -- they keep the separate kernel (CE_GPU_FUSED_OUTPUT=2 forces it on).
-  const bool lsm = (m->kind == kKindI8 ? m->fused_output != 0 : m->fused_output == 2) && NP % 4 == 0 && !Dl.meta.relu && Dl.meta.batchnorm < 0 && m->keep_acc != nb - 1 &&
+  const bool lsm = (m->kind == kKindI8 ? m->fused_output != 0 : m->fused_output == 2) && NP % 4 == 0 &&
+                   (lsm_dense || m->prog.log_softmax) &&   // (selection without a LogSoftmax layer: nothing to fuse)
+                   !Dl.meta.relu && Dl.meta.batchnorm < 0 && m->keep_acc != nb - 1 &&
                    (!lsm_dense || loglik_dev == nullptr || (reinterpret_cast<uintptr_t>(loglik_dev) & 15) == 0);
   HostMark("chunk: first quantize");
   for (int b = 0; b < nb; ++b) {
@@ -728,11 +731,16 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
         a.lsm_out_row_off = w->outrow_table.dev<int64_t>();     // absolute frame index over the batch
         a.lsm_out_rows = out_off[n_utts];
         a.lsm_argmax = argmax_dev;
-      } else {                                           // finished rows in row space, selected below
+      } else {
+        // selecting outputs: ONE sweep writes the plain logits in row space plus every row's log-sum-exp
+        // -- reduced exactly as the dense fused output reduces it, so that selected and dense rows agree
+        // bit for bit -- and the selecting kernel below subtracts it
         a.out_f32 = w->logits.as<float>();
         a.ld_out = ldp;
         a.lsm_rowspace = 1;
         a.lsm_out_rows = M;
+        a.lsm_single = 1;
+        a.lsm_lse_out = w->row_lse.as<float>();
       }
     }
     if (s_gemm != s) {
@@ -758,9 +766,9 @@ int ForwardChunk(ce_gpu_model *m, ce_gpu_model::ChunkWs *w, const PcmSource &src
   HostMark("chunk: quantize launches");
   if (lsm && lsm_dense) return CE_GPU_OK;
   CE_CHECK(FinalizeLaunch(w->logits.as<float>(), ldp, NP, M, d_tile, d_utts,
-                          w->outrow_table.dev<int64_t>(), L, R, lsm ? false : m->prog.log_softmax,
-                          lsm ? m->zero_prior.as<float>() : m->log_prior.as<float>(), loglik_dev, m->out_words(),
-                          argmax_dev, s, m->out_sel));
+                          w->outrow_table.dev<int64_t>(), L, R, m->prog.log_softmax, m->log_prior.as<float>(),
+                          loglik_dev, m->out_words(), argmax_dev, s, m->out_sel,
+                          lsm ? w->row_lse.as<float>() : nullptr));
   HostMark("chunk: finalize");
   return CE_GPU_OK;
 }

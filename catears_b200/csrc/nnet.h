@@ -64,7 +64,7 @@ struct ce_gpu_model {
     ce::DevBuf feats;                  // this chunk's fbank output [frames x feat_dim]
     ce::Table fbank_chunks;
     ce::DevBuf x0;                     // padded fp32 input [M x feat_dim]
-    ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits;
+    ce::DevBuf act_f32[2], act_lo[2], act_bf16[2], act_u8, rowsum, logits, row_lse;
     ce::DevBuf minmax, qparams;
     ce::DevBuf stage_loglik;
     ce::Table cmvn_utts, utt_table, tile_table, outrow_table;

@@ -519,7 +519,8 @@ finalize_rowcache_kernel(const float *__restrict__ logits, int64_t ld, int N, in
 // The finished row of one warp: NV float4 per lane, column 4 (i 32 + lane) + q; padding = -FLT_MAX.
 template <int NV>
 __device__ __forceinline__ void FinalRow(const float *__restrict__ x, int N, int lane, int log_softmax,
-                                         const float *__restrict__ log_prior, float4 (&v)[NV]) {
+                                         const float *__restrict__ log_prior, float4 (&v)[NV],
+                                         const float *__restrict__ lse_row = nullptr) {
   const float4 *x4 = reinterpret_cast<const float4 *>(x);
   const float4 *lp4 = reinterpret_cast<const float4 *>(log_prior);
   const int n4 = N >> 2;
@@ -529,7 +530,11 @@ __device__ __forceinline__ void FinalRow(const float *__restrict__ x, int N, int
     v[i] = (c < n4) ? __ldcs(x4 + c) : make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
   }
   float lse = 0.0f;
-  if (log_softmax) {
+  if (log_softmax && lse_row) {
+    // the row's log-sum-exp as the output layer's own epilogue reduced it (GemmArgs::lsm_single): the same
+    // number the fused dense output subtracts, so selected and dense rows agree bit for bit
+    lse = __ldg(lse_row);
+  } else if (log_softmax) {
     float m = -FLT_MAX;
 #pragma unroll
     for (int i = 0; i < NV; ++i) m = fmaxf(fmaxf(fmaxf(m, v[i].x), fmaxf(v[i].y, v[i].z)), v[i].w);
@@ -585,7 +590,8 @@ finalize_subset_kernel(const float *__restrict__ logits, int64_t ld, int N, int 
                        const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
                        const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
                        const float *__restrict__ log_prior, const int32_t *__restrict__ ids, int n_ids,
-                       float *__restrict__ out, int64_t ld_out, int32_t *__restrict__ argmax) {
+                       float *__restrict__ out, int64_t ld_out, int32_t *__restrict__ argmax,
+                       const float *__restrict__ lse_in) {
   extern __shared__ float4 s_rows4[];
   const int lane = threadIdx.x & 31;
   const int n4 = N >> 2;
@@ -597,7 +603,7 @@ finalize_subset_kernel(const float *__restrict__ logits, int64_t ld, int N, int 
     const int64_t orow = OutputRowOf(row, tile_utt, utts, out_row_off, left, right);
     if (orow < 0) continue;
     float4 v[NV];
-    FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v);
+    FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v, lse_in ? lse_in + row : nullptr);
     float best = -FLT_MAX;
     int best_i = 0x7fffffff;
 #pragma unroll
@@ -675,7 +681,8 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
                      const int32_t *__restrict__ tile_utt, const UttRows *__restrict__ utts,
                      const int64_t *__restrict__ out_row_off, int left, int right, int log_softmax,
                      const float *__restrict__ log_prior, int k, int limit, int cap,
-                     uint2 *__restrict__ out, int64_t ld_out_pairs, int32_t *__restrict__ argmax) {
+                     uint2 *__restrict__ out, int64_t ld_out_pairs, int32_t *__restrict__ argmax,
+                     const float *__restrict__ lse_in) {
   extern __shared__ unsigned long long s_list_all[];
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -689,7 +696,7 @@ finalize_topk_kernel(const float *__restrict__ logits, int64_t ld, int N, int M,
     uint32_t key[4 * NV];
     {
       float4 v[NV];
-      FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v);
+      FinalRow<NV>(logits + (int64_t)row * ld, N, lane, log_softmax, log_prior, v, lse_in ? lse_in + row : nullptr);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const bool in = i * 32 + lane < n4;              // padding sorts below every real entry
@@ -912,7 +919,7 @@ int ConvertLaunch(const float *x, int64_t ld_in, int C, int64_t M, int c_pad,
 int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
                    const UttRows *utts, const int64_t *out_row_off, int left, int right,
                    bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
-                   int32_t *argmax, cudaStream_t s, const OutSel &sel) {
+                   int32_t *argmax, cudaStream_t s, const OutSel &sel, const float *lse_in) {
   if (M <= 0) return CE_GPU_OK;
   ProfScope prof(kProfFinalize, s);
   const unsigned fgrid = (unsigned)std::min((M + 3) / 4, 32 * SmCount());
@@ -938,7 +945,8 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     finalize_topk_kernel<NV, MT><<<fgrid, 128, smem, s>>>(                                        \
         logits, ld, N, M, tile_utt, utts, out_row_off, left, right, log_softmax ? 1 : 0,          \
-        log_prior, sel.n, limit, cap, reinterpret_cast<uint2 *>(loglik), ld_out / 2, argmax);     \
+        log_prior, sel.n, limit, cap, reinterpret_cast<uint2 *>(loglik), ld_out / 2, argmax,      \
+        lse_in);                                                                                  \
   } while (0)
 #define CE_FINALIZE_SEL(NV)                                                                       \
   do {                                                                                            \
@@ -948,7 +956,7 @@ int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t 
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       finalize_subset_kernel<NV><<<fgrid, 128, smem, s>>>(                                        \
           logits, ld, N, M, tile_utt, utts, out_row_off, left, right, log_softmax ? 1 : 0,        \
-          log_prior, sel.ids, sel.n, loglik, ld_out, argmax);                                     \
+          log_prior, sel.ids, sel.n, loglik, ld_out, argmax, lse_in);                             \
     } else if (sel.n <= 32) {                                                                     \
       CE_FINALIZE_TOPK(NV, 2);                                                                    \
     } else if (sel.n <= 64) {                                                                     \

@@ -45,7 +45,8 @@ constexpr int kMaxTopK = 1024;
 int FinalizeLaunch(const float *logits, int64_t ld, int N, int M, const int32_t *tile_utt,
                    const UttRows *utts, const int64_t *out_row_off, int left, int right,
                    bool log_softmax, const float *log_prior, float *loglik, int64_t ld_out,
-                   int32_t *argmax, cudaStream_t s, const OutSel &sel = OutSel());
+                   int32_t *argmax, cudaStream_t s, const OutSel &sel = OutSel(),
+                   const float *lse_in = nullptr);   // [M] log-sum-exp of every row, already reduced (selecting kernels)
 
 }  // namespace ce
 #endif  // CE_GPU_NNET_KERNELS_H_

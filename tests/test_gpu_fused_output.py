@@ -60,8 +60,9 @@ def test_fused_equals_separate(small_model, port, precision, fused):
 
 
 def test_fused_argmax_only_and_selected_rows(small_model):
-    """loglik = None (argmax only: the second sweep writes nothing) and the selecting outputs (the fused layer
-    writes finished rows in row space, the selection kernels pick from them): bit-identical to the dense rows."""
+    """loglik = None (argmax only: the second sweep writes nothing) and the selecting outputs (ONE sweep of the
+    fused layer writes plain logits in row space plus every row's log-sum-exp, the selection kernels subtract
+    that very number): bit-identical to the dense rows."""
     rng = np.random.default_rng(12)
     m = load(small_model["conf"], "int8", 1)
     try:
