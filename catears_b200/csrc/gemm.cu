@@ -643,7 +643,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
           for (int tap = 0; tap < p.n_taps; ++tap) {
             const int row = m0 + p.tap_off[tap];
             for (int kb = 0; kb < kb_per_tap; ++kb) {
+#ifdef CE_PRODUCER_RELAXED
+              mbar_wait_relaxed(bar_empty + 8 * stage, phase ^ 1);
+#else
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+#endif
               if (p.debug & 4) {
                 if (leader) mbar_arrive(bar_full + 8 * stage);
               } else if (CG == 1) {

@@ -82,3 +82,34 @@ def test_fused_argmax_only_and_selected_rows(small_model):
         assert np.array_equal(sub, ll[:, ids])
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("num_pdfs", [4, 52, 100, 260, 516, 98])
+def test_fused_ragged_widths(tmp_path, port, num_pdfs):
+    """Output widths that end inside a 16-column piece, inside a 64-column part and just behind a 256-column
+    tile (the last piece's masks, the TMA store's column clipping, warps with nothing to do); 98 is not a
+    multiple of 4 and takes the separate kernel.  int8, against the oracle and against the separate kernel."""
+    from catears_b200 import synth
+    m = synth.write_model(str(tmp_path / "w"), name="w%d" % num_pdfs, hidden=64, num_pdfs=num_pdfs, seed=500 + num_pdfs)
+    prior = F.read_vector(m["prior"])
+    rng = np.random.default_rng(num_pdfs)
+    a = load(m["conf"], "int8", 1)
+    b = load(m["conf"], "int8", 0)
+    try:
+        x, off = ragged_batch(rng, [70, 1, 140])
+        la, aa = a.nnet(x, off)
+        lb, ab = b.nnet(x, off)
+        assert la.shape == (211, num_pdfs)
+        assert np.abs(la - lb).max() < 5e-6
+        assert np.array_equal(aa, la.argmax(axis=1))
+        want = port.am_forward(m["nnet"], prior, m["left"], m["right"], x[:70], mode="u8")
+        assert np.abs(la[:70] - want).max() < 1e-5
+        if num_pdfs >= 8 and num_pdfs % 4 == 0:             # (the selecting outputs need num_pdfs % 4 == 0)
+            a.set_output("topk", k=3)
+            best, _ = a.nnet(x, off)
+            order = np.argsort(-la, axis=1, kind="stable")[:, :3]
+            assert np.array_equal(best["pdf"], order.astype(np.int32))
+            assert np.array_equal(best["loglik"], np.take_along_axis(la, order, axis=1))
+    finally:
+        a.close()
+        b.close()
