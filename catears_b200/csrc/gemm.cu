@@ -1217,16 +1217,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
             scale_q[g] = __fmul_rn(q.scale, p.scale_b);                 // matrix.cc:403 (float * float)
           }
         }
-        // per row: 4 rows a lane, row group j = accumulator quadrant j
+        // per row: 4 rows a lane, row group j = accumulator quadrant j.  All row-sum loads of the tile
+        // (4 rows x taps) are issued before the first one is used: as a loop over the taps they ran one
+        // after the other and the first layer's epilogue (5 taps) waited a fifth of its time for them.
+        int32_t rs[4][kMaxTaps];
+        if (KIND == kKindI8) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int t = 0; t < kMaxTaps; ++t) {
+              const int r = m0 + 32 * j + lane + p.tap_off[t < p.n_taps ? t : 0];
+              rs[j][t] = (t < p.n_taps && r >= 0 && r < p.M) ? __ldg(p.a_rowsum + r) : 0;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int row = m0 + 32 * j + lane;
           int32_t rsum = 0;
           if (KIND == kKindI8) {
-            for (int t = 0; t < p.n_taps; ++t) {
-              const int r = row + p.tap_off[t];
-              if (r >= 0 && r < p.M) rsum += __ldg(p.a_rowsum + r);
-            }
+#pragma unroll
+            for (int t = 0; t < kMaxTaps; ++t) rsum += rs[j][t];
           }
           row_corr[j] = p.zp_b * rsum;
           int flag = 0;
