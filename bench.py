@@ -501,7 +501,12 @@ def run_gpu(args):
             "; the fp32 path spends 3 tf32 passes per product" if args.precision == "fp32" else "", peak_src)
     gemm_ms, gemm_n = prof["gemm"]
     fb_ms, fb_n = prof["fbank"]
-    flops_step = frames * FLOPS_PER_FRAME          # this rank's share
+    # int8 models: the output layer runs fused with LogSoftmax + prior + argmax and is timed in the "finalize"
+    # category (the library's rule, catears_b200/csrc/nnet.cc); the roofline's dominant kernel is then the
+    # plain GEMM of the other six layers, and the fused launch gets its own object below
+    fused_out = args.precision == "int8" and os.environ.get("CE_GPU_FUSED_OUTPUT", "1") != "0"
+    flops_out = 2.0 * 1024 * model.num_pdfs        # the output layer's share of FLOPS_PER_FRAME
+    flops_step = frames * (FLOPS_PER_FRAME - flops_out if fused_out else FLOPS_PER_FRAME)   # this rank's share
     traffic = hbm_step = pipe_ncu = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
@@ -512,7 +517,7 @@ def run_gpu(args):
             # rows per 10 s utterance) of the average GEMM launch, times the rows one launch of this
             # run's chunking covers
             launches_per_step = gemm_n / max(1, args.steps)
-            traffic = int(per_row * n_utts * 1024 / max(1.0, launches_per_step / 7.0))
+            traffic = int(per_row * n_utts * 1024 / max(1.0, launches_per_step / (6.0 if fused_out else 7.0)))
         if args.precision == "int8" and tr.get("step_int8_dram_bytes_per_row"):
             hbm_step = int(tr["step_int8_dram_bytes_per_row"] * n_utts * 1024)
         pipe_ncu = tr.get("gemm_%s_tensor_pipe_active_pct" % args.precision)
@@ -530,11 +535,26 @@ def run_gpu(args):
         "share_of_step": round(gemm_ms / ms_serial, 4),
         "timing": "CUDA events around every launch in a second pass of the same steps "
                   "(%.3f ms/step with the events in)" % (ms_serial / args.steps),
-        "note": "the last launch of every pass is the output layer fused with LogSoftmax + prior + argmax: it "
-                "multiplies its tiles twice (row statistics, then the finished rows) and its time contains what "
-                "the separate log-softmax kernel used to take (kernel_ms_per_step.finalize = 0); `achieved` "
-                "counts the algorithmic FLOPs once",
+        "note": ("the six layers in front of the output layer; the output layer runs fused with LogSoftmax + prior + "
+                 "argmax and is timed as kernel_ms_per_step.finalize (roofline_output)") if fused_out else
+                "all seven layers; log-softmax is a separate launch (kernel_ms_per_step.finalize)",
     }
+    roofline_output = None
+    fin_ms, fin_n = prof["finalize"]
+    if fused_out and fin_ms > 0:
+        out_tflops = frames * flops_out * args.steps / (fin_ms * 1e-3) / 1e12
+        out_gbs = frames * 4.0 * model.num_pdfs * args.steps / (fin_ms * 1e-3) / 1e9
+        roofline_output = {
+            "kernel": "gemm_kernel<int8, LSM> (output layer + LogSoftmax + prior + argmax, %d launches/step)"
+                      % (fin_n // max(1, args.steps)),
+            "bound": "tensor", "achieved": round(out_tflops, 2), "peak": round(tensor_peak, 1), "unit": "TFLOP/s",
+            "frac": round(out_tflops / tensor_peak, 4),
+            "hbm_write_gbs": round(out_gbs, 1), "hbm_write_frac": round(out_gbs / hbm_peak, 4),
+            "avg_launch_ms": round(fin_ms / max(1, fin_n), 4), "share_of_step": round(fin_ms / ms_serial, 4),
+            "note": "algorithmic FLOPs counted once: the kernel multiplies every tile twice (row statistics, then the "
+                    "finished rows) instead of writing and re-reading 4 x 3072 B of logits per frame; its epilogue "
+                    "(2 x 3072 accumulator columns per row) and shared-memory bandwidth bound it, not the tensor "
+                    "pipe (DESIGN.md 5.3: MMA floor 507 us, epilogue alone 551 us, together 694 us per 131072 rows)"}
     fb_gbs = frames * FBANK_BYTES_PER_FRAME * args.steps / (fb_ms * 1e-3) / 1e9 if fb_ms > 0 else 0.0
     roofline_fbank = {"kernel": "fbank_kernel", "bound": "hbm", "achieved": round(fb_gbs, 1),
                       "peak": hbm_peak, "unit": "GB/s", "frac": round(fb_gbs / hbm_peak, 4),
@@ -561,7 +581,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(frames * 4) * world,
                 "note": "pinned host PCM in, per-frame argmax out; log-likelihoods stay in HBM (H6)"},
         "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_fbank": roofline_fbank,
+        "roofline": roofline, "roofline_output": roofline_output, "roofline_fbank": roofline_fbank,
         "kernel_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
     }
     if hbm_step is not None:

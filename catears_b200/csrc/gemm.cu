@@ -1508,7 +1508,7 @@ int LaunchKind(const GemmOperands &ops, const GemmArgs &args, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ProfScope prof(kProfGemm, s);
+  ProfScope prof(LSM ? kProfFinalize : kProfGemm, s);    // the fused output layer IS the log-softmax launch now
   CE_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<KIND, CG, GRAN, MODE>, ma0, ma1, mb0, mb1, mo0, mo1, args));
   CE_LAUNCHED();
   return CE_GPU_OK;

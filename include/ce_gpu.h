@@ -303,7 +303,7 @@ int64_t ce_gpu_launch_count(int reset);
 
 /* Per-category device timing of the kernels launched by this thread (CUDA events on the
  * launching stream; off by default).  Categories: 0 fbank, 1 cmvn(+pad), 2 GEMM, 3 min/max +
- * quantise, 4 log-softmax/prior/argmax, 5 other.  ce_gpu_profile_read waits for the recorded
+ * quantise, 4 log-softmax/prior/argmax (int8 models: the output layer's GEMM fused with them), 5 other.  ce_gpu_profile_read waits for the recorded
  * launches, returns the summed milliseconds and launch counts (arrays of 6) and clears them. */
 #define CE_GPU_PROFILE_CATEGORIES 6
 int ce_gpu_profile_enable(int on);

@@ -21,7 +21,12 @@ def main():
     rd = list(csv.DictReader(lines))
     per = {}
     for r in rd:
-        k = r["Kernel Name"].split("(")[0].split("<")[0].split("::")[-1]
+        full = r["Kernel Name"].split("(")[0]
+        k = full.split("<")[0].split("::")[-1]
+        if k == "gemm_kernel" and "<" in full:             # gemm_kernel<KIND, CG, GRAN, MODE>: MODE 1 = the output
+            targs = full.split("<", 1)[1].rstrip(">").split(",")   # layer fused with LogSoftmax + prior + argmax
+            if len(targs) >= 4 and targs[3].strip() == "1":
+                k = "gemm_kernel_lsm"
         d = per.setdefault((r["ID"], k), {})
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"]
