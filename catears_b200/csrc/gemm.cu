@@ -1592,11 +1592,14 @@ int GemmLaunch(int kind, const GemmOperands &ops, const GemmArgs &args_in, cudaS
       }
     }
   }
-  // CE_GPU_WIDE_EPILOGUE=1: plain int8 layers with the fused output layer's 16-warp epilogue (kModeWide).
-  // Bit-exact (the whole GPU suite passes with it) and a little faster per launch under ncu (first layer 192 ->
-  // 183 us, hidden layers 280 -> 274 us per 131072 rows), but SLOWER in the timed step, which runs into the
-  // power cap: GEMMs 9.61 ms against 9.26 ms per 512-utterance step (A/B in one run) -- off by default.
-  static const bool wide_on = getenv("CE_GPU_WIDE_EPILOGUE") && atoi(getenv("CE_GPU_WIDE_EPILOGUE")) != 0;
+  // kModeWide: plain int8 layers through the fused output layer's 16-warp epilogue.  Bit-exact (the whole GPU
+  // suite passes with it on every layer, CE_GPU_WIDE_EPILOGUE=1), but only worth it where the epilogue is the
+  // bound: layers whose K fits two pipeline stages (the first layer, K = 200: 160 -> 148 us per 131072 rows,
+  // GEMMs 6.37 -> 6.20 ms per step) -- the default, CE_GPU_WIDE_EPILOGUE=2.  On the hidden layers, which are bound
+  // by the multiplications, it is a little faster per launch under ncu (280 -> 274 us) and SLOWER in the timed
+  // step, which runs into the power cap (9.61 against 9.26 ms with it on every layer).  0 = never.
+  static const int wide_env = getenv("CE_GPU_WIDE_EPILOGUE") ? atoi(getenv("CE_GPU_WIDE_EPILOGUE")) : 2;
+  const bool wide_on = wide_env == 1 || (wide_env == 2 && (int64_t)args.n_taps * args.c_pad <= 2 * kTileKBytes);
   if (wide_on && kind == kKindI8 && cta_group != 1 && args.out_f32 && !args.out_acc && !args.out_lo)
     return gran ? LaunchKind<kKindI8, 2, true, kModeWide>(ops, args, s) : LaunchKind<kKindI8, 2, false, kModeWide>(ops, args, s);
   if (cta_group == 1) {
