@@ -9,18 +9,23 @@
 //   bias / ReLU / BatchNorm     src/nnet.cc:34,149-160,106-117
 //   FindMinMax of the result    src/matrix.cc:329-345 (input of the next layer's Quantize)
 //
-// Structure (Blackwell-native): persistent CTAs, one per SM, 6 warps:
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of A [128 rows x 128 B]
-//               and B [256 rows x 128 B] into a 4-stage shared-memory ring, mbarrier-signalled;
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (cta_group::1, M=128, N=256,
-//               K = 32 bytes per instruction) with the accumulator in tensor memory;
-//               two 256-column accumulator stages so tile i+1 is multiplied while tile i drains;
-//   warps 2-5   epilogue: tcgen05.ld of the accumulator (one TMEM lane quadrant per warp),
-//               the exact fp32 chain of the reference (un-fused multiplies/adds, its order),
-//               transpose through shared memory, coalesced 128-byte row stores.
-// Data paths: kind::i8 (u8 x u8 -> s32, the zero-point algebra of gemmlowp applied to the exact
-// raw sums), kind::f16 (bf16 -> fp32) and kind::tf32 (optionally three passes hi*hi + hi*lo +
-// lo*hi for fp32-class accuracy).
+//   LogSoftmax + prior + argmax src/nnet.cc:137-146, src/vector.cc:110-122, src/am.cc:109-112 (kModeLsm: fused
+//                               into the output layer's epilogue, int8 models)
+//
+// Structure (Blackwell-native): persistent CTAs, one per SM (a pair per TPC with cta_group::2):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128B swizzle) of A [128 rows x 128 B] and the
+//               CTA's share of B into a 5-stage shared-memory ring, mbarrier-signalled;
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (cta_group::2: M = 256 over the pair, N = 256,
+//               K = 32 bytes per instruction) with the accumulator in tensor memory; two 256-column
+//               accumulator stages so tile i+1 is multiplied while tile i drains;
+//   warps 2..   epilogue: tcgen05.ld of the accumulator (one TMEM lane quadrant per warp), the exact fp32 chain
+//               of the reference (un-fused multiplies/adds, its order), swizzled staging tile, TMA store.
+//               kModeClassic: 8 warps on 32-column chunks (every kind / output format); kModeWide / kModeLsm:
+//               16 warps on 16-column pieces with packed f32x2 arithmetic (int8);
+//   last warp   parameter prefetcher: per-tile epilogue parameters one tile ahead in two shared-memory slots.
+// Data paths: kind::i8 (u8 x u8 -> s32, the zero-point algebra of gemmlowp applied to the exact raw sums),
+// kind::f16 (bf16 -> fp32; bf16x3 = hi/lo split operands) and kind::tf32 (optionally three passes hi*hi +
+// hi*lo + lo*hi for fp32-class accuracy).
 
 #include "gemm.h"
 
