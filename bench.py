@@ -714,6 +714,13 @@ def run_longform(args):
     # the online CMVN is a sequential chain per utterance, so one 45 000-frame shard per GPU would
     # serialise on a single CTA; ~90 shards cost 15 % halo recomputation and run like a batch.
     n_shards = max(world, (total + 4095) // 4096)
+    if args.exact:
+        # --exact: the hour as ONE utterance -- the online CMVN chain runs from the first frame (bit-identical to
+        # the reference's frame-by-frame evaluation of the whole stream: no warm-up halo, no fp32-rounding
+        # difference), its bins spread over ten CTAs; single GPU (the chain cannot be cut across GPUs exactly)
+        if world > 1:
+            raise SystemExit("--workload longform --exact runs on one GPU")
+        n_shards = 1
     kb, ke, fb, fe = api.time_shards(total, n_shards, model.left_context, model.right_context, 600)
     mine = list(range(n_shards * rank // world, n_shards * (rank + 1) // world))
     parts, off = [], [0]
@@ -794,7 +801,8 @@ def run_longform(args):
             "data": "synthetic",
             "config": {"workload": "config 5: one hour of 16 kHz audio (%d frames) in %d time shards with "
                                    "recomputed halos (L + 600 CMVN-history frames before, R after), %d shard(s) "
-                                   "per GPU as one batch (%d frames fed), fbank + CMVN + TDNN, %s GEMMs; %s"
+                                   "per GPU as one batch (%d frames fed; 1 shard = the whole stream as one utterance, "
+                                   "exact online CMVN), fbank + CMVN + TDNN, %s GEMMs; %s"
                                    % (total, n_shards, len(mine), fed, args.precision,
                                       "rows to a host consumer pool" if feed else "log-likelihoods stay in HBM"),
                        "frames_per_step": total,
@@ -886,6 +894,8 @@ def main():
     ap.add_argument("--feed", default="none", choices=["none", "topk"],
                     help="longform: rows to pinned host memory + a pool of consumer threads (config 5's decoder feed)")
     ap.add_argument("--feed-topk", type=int, default=64)
+    ap.add_argument("--exact", action="store_true",
+                    help="longform: the whole stream as one utterance (exact online CMVN, one GPU)")
     ap.add_argument("--feed-threads", type=int, default=8)
     ap.add_argument("--streams", type=int, default=512)
     ap.add_argument("--stream-ms", type=int, default=100)

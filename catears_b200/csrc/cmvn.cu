@@ -47,35 +47,43 @@ struct CmvnStep {    // frame-index-only part of the chain (t < 600; t >= 599 us
 
 constexpr int kCmvnThreads = 256;
 
-// Shared memory: x[2][TF][mel], xo[2][TF][mel], S[2][TF][mel] floats.
+// One CTA = one utterance x one group of `nb_per` consecutive mel bins (all of them when the batch has enough
+// utterances to fill the GPU; groups of 8 for a few long utterances, so that an hour-long stream spreads over
+// several SMs and its tiles get long: the chain of a bin is sequential, its bins are not).
+// Shared memory: x[2][TF][nb], d[2][TF][nb] (x_t - x_{t-600}), S[2][TF][nb] floats, then inexact[2].
+// NBT: nb_per as a compile-time constant (the chain's loads and stores then take immediate offsets), 0 = any.
+template <int NBT>
 __global__ void __launch_bounds__(kCmvnThreads)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
-            int mel, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
+            int mel, int nb_per, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
             int64_t out_stride, float *__restrict__ state, uint32_t *__restrict__ minmax) {
   extern __shared__ float cmvn_smem[];
   const CmvnUtt ut = utts[blockIdx.x];
   const int T = ut.T;
   if (T <= 0) return;
+  const int b0 = blockIdx.y * nb_per;            // this CTA's bins [b0, b0 + nb)
+  const int nb = min(nb_per, mel - b0);
   const int tb = ut.t_base;                    // absolute index of this launch's first frame
   const int TF = tile_frames;
-  const int tile_elems = TF * mel;
+  const int tile_elems = TF * nb_per;
   float *xs = cmvn_smem;                         // [2][tile_elems]
-  float *xos = cmvn_smem + 2 * tile_elems;       // [2][tile_elems]
+  float *dds = cmvn_smem + 2 * tile_elems;       // [2][tile_elems]
   float *ss = cmvn_smem + 4 * tile_elems;        // [2][tile_elems]
+  int *inexact = reinterpret_cast<int *>(cmvn_smem + 6 * tile_elems);   // [2]: some x - x_old of the tile is not exact
   const bool apply = g != nullptr;
-  const int chain_threads = apply ? ((mel + 31) / 32) * 32 : 0;   // whole warps
+  const int chain_threads = apply ? ((nb_per + 31) / 32) * 32 : 0;   // whole warps
   const int tid = threadIdx.x;
   const bool is_chain = tid < chain_threads;
   const int wtid = tid - chain_threads;          // index among the loader/output threads
   const int n_workers = kCmvnThreads - chain_threads;
-  const float *x = feats + ut.in_row * mel;
-  float *y = out + (ut.out_row + pad_left) * out_stride;
+  const float *x = feats + ut.in_row * mel + b0;
+  float *y = out + (ut.out_row + pad_left) * out_stride + b0;
   const int n_tiles = (T + TF - 1) / TF;
 
-  // Workers index a tile flat (it is contiguous in feats); i / mel by multiply-shift (i < 2^13,
-  // mel <= 128: exact with a 20-bit reciprocal).  Every load of a tile is issued before any is used.
-  const uint32_t inv_mel = ((1u << 20) + mel - 1) / mel;
+  // Workers index a tile flat, element i = (frame i / nb, bin i % nb); i / nb by multiply-shift (i < 2^13,
+  // nb <= 128: exact with a 20-bit reciprocal).  Every load of a tile is issued before any is used.
+  const uint32_t inv_nb = ((1u << 20) + nb - 1) / nb;
   constexpr int kPerThread = 16;                 // >= tile_elems / n_workers for every configuration
   // Loading a tile is split in two so that its latency hides behind the stores of the previous tile:
   // fetch_tile issues every load into registers, commit_tile writes them to shared memory once the
@@ -83,48 +91,63 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   float la[kPerThread], lb[kPerThread];
   auto fetch_tile = [&](int j) {                 // workers: global -> registers, tile j
     const int t0 = j * TF;
-    const int n = min(TF, T - t0) * mel;
+    const int n = min(TF, T - t0) * nb;
     const float *src = x + (int64_t)t0 * mel;
     const bool need_old = apply && tb + t0 + TF > kCmvnWindow;   // some frame of the tile has t >= 600
-    const int first_old = (kCmvnWindow - tb - t0) * mel;         // elements before it have t < 600
+    const int first_old = kCmvnWindow - tb - t0;                 // tile frames before it have t < 600
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
       const int i = wtid + k * n_workers;
-      la[k] = (i < n) ? __ldg(src + i) : 0.0f;
-      lb[k] = (need_old && i < n && i >= first_old) ? __ldg(src + i - kCmvnWindow * mel) : 0.0f;
+      const int tl = (int)(((uint32_t)i * inv_nb) >> 20), d = i - tl * nb;
+      const int64_t o = (int64_t)tl * mel + d;
+      la[k] = (i < n) ? __ldg(src + o) : 0.0f;
+      lb[k] = (need_old && i < n && tl >= first_old) ? __ldg(src + o - (int64_t)kCmvnWindow * mel) : 0.0f;
     }
     asm volatile("" ::: "memory");               // the loads are issued here, not where they are used
   };
+  // The reference's  S = float(double(S) + x - x_old)  (cmvn.cc:42-47,63-67) without fp64, whose
+  // CUDA-core rate on this part makes a dependent chain cost ~280 clocks per frame: the double sums
+  // are exact (24-bit operands a few binades apart), so S is the correctly rounded three-term sum.
+  // With d = x - x_old: if the subtraction is exact (its TwoSum error term is zero -- always, for
+  // log-mel magnitudes) the result is RN(S + d), one fp32 add; otherwise the tile falls back to fp64.
+  // For t < 600 it is RN(S + x) (x_old = 0).  The differences and the exactness test are element-wise,
+  // so the WORKERS make them while they stage the tile; only the add is left on the dependent chain.
   auto commit_tile = [&](int j) {                // workers: registers -> smem, tile j
     const int t0 = j * TF;
-    const int n = min(TF, T - t0) * mel;
+    const int n = min(TF, T - t0) * nb;
     float *dx = xs + (j & 1) * tile_elems;
-    float *dxo = xos + (j & 1) * tile_elems;
-    const bool need_old = apply && tb + t0 + TF > kCmvnWindow;
+    float *dd = dds + (j & 1) * tile_elems;
+    bool bad = false;
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
       const int i = wtid + k * n_workers;
       if (i < n) {
-        dx[i] = la[k];
-        if (need_old) dxo[i] = lb[k];
+        const float xv = la[k], xo = lb[k];
+        const float dh = __fsub_rn(xv, xo);                            // TwoSum(x, -x_old)
+        const float bv = __fsub_rn(dh, xv);
+        const float dl = __fadd_rn(__fsub_rn(xv, __fsub_rn(dh, bv)), __fsub_rn(-xo, bv));
+        bad |= dl != 0.0f;
+        dx[i] = xv;
+        dd[i] = dh;
       }
     }
+    if (apply && bad) inexact[j & 1] = 1;
   };
   float wmin = FLT_MAX, wmax = -FLT_MAX;         // FindMinMax of what this thread writes (matrix.cc:329-345)
   auto store_tile = [&](int j) {                 // workers: y for tile j, and the replicated edges
     const int t0 = j * TF;
-    const int n = min(TF, T - t0) * mel;
+    const int n = min(TF, T - t0) * nb;
     const float *dx = xs + (j & 1) * tile_elems;
     const float *ds = ss + (j & 1) * tile_elems;
 #pragma unroll 4
     for (int i = wtid; i < n; i += n_workers) {
-      const int tl = (int)(((uint32_t)i * inv_mel) >> 20), d = i - tl * mel;
+      const int tl = (int)(((uint32_t)i * inv_nb) >> 20), d = i - tl * nb;
       const int t = t0 + tl;
       float r = dx[i];
       if (apply) {
         const CmvnStep st = steps[min(tb + t, kCmvnWindow - 1)];
         float stat = ds[i];
-        if (tb + t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, __ldg(g + d)));   // AddVec
+        if (tb + t < kCmvnWindow - 1) stat = __fadd_rn(stat, __fmul_rn(st.alpha, __ldg(g + b0 + d)));   // AddVec
         r = __fadd_rn(r, __fmul_rn(st.nscale, stat));                                       // cmvn.cc:96-97
       }
       y[(int64_t)t * out_stride + d] = r;
@@ -137,14 +160,10 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
     }
   };
 
-  // The reference's  S = float(double(S) + x - x_old)  (cmvn.cc:42-47,63-67) without fp64, whose
-  // CUDA-core rate on this part makes a dependent chain cost ~280 clocks per frame: the double sums
-  // are exact (24-bit operands a few binades apart), so S is the correctly rounded three-term sum.
-  // With d = x - x_old: if the subtraction is exact (its TwoSum error term is zero -- always, for
-  // log-mel magnitudes) the result is RN(S + d), one fp32 add; otherwise fall back to fp64.  For
-  // t < 600 it is RN(S + x).  Only that add is on the dependent chain.
   float cached = 0.0f;                           // chain state of this thread's bin
-  if (state && is_chain && tid < mel) cached = state[(int64_t)blockIdx.x * mel + tid];   // streaming: resume
+  if (state && is_chain && tid < nb) cached = state[(int64_t)blockIdx.x * mel + b0 + tid];   // streaming: resume
+  if (tid < 2) inexact[tid] = 0;
+  __syncthreads();
   if (!is_chain) {
     fetch_tile(0);
     commit_tile(0);
@@ -152,52 +171,71 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
   __syncthreads();
   for (int j = 0; j < n_tiles; ++j) {
     if (is_chain) {
-      if (tid < mel) {
+      if (tid < nb) {
         const int t0 = j * TF;
         const int nt = min(TF, T - t0);
-        const float *dx = xs + (j & 1) * tile_elems + tid;
-        const float *dxo = xos + (j & 1) * tile_elems + tid;
+        const float *dd = dds + (j & 1) * tile_elems + tid;
         float *ds = ss + (j & 1) * tile_elems + tid;
-        if (tb + t0 + TF <= kCmvnWindow) {       // no frame leaves the window yet
-#pragma unroll 8
-          for (int tl = 0; tl < nt; ++tl) {
-            cached = __fadd_rn(cached, dx[tl * mel]);
-            ds[tl * mel] = cached;
+        if (!inexact[j & 1]) {                   // (always, for log-mel features)
+          // 16 differences are in registers before the first sum is stored, and the next 16 are on their
+          // way while these are added: as a plain loop every load waited behind the store before it (the
+          // compiler must assume they alias) and a frame cost ~140 clocks; only the add is sequential.
+          constexpr int kBatch = 16;
+          const int st = NBT ? NBT : nb;         // floats between consecutive frames of a bin
+          int tl0 = 0;
+          float v[kBatch], w[kBatch];
+          if (nt >= kBatch) {
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) v[u] = dd[u * st];
           }
-        } else {
-#pragma unroll 8
+          for (; tl0 + kBatch <= nt; tl0 += kBatch) {
+            const bool more = tl0 + 2 * kBatch <= nt;
+            if (more) {
+#pragma unroll
+              for (int u = 0; u < kBatch; ++u) w[u] = dd[(tl0 + kBatch + u) * st];
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              cached = __fadd_rn(cached, v[u]);
+              ds[(tl0 + u) * st] = cached;
+            }
+            if (more) {
+#pragma unroll
+              for (int u = 0; u < kBatch; ++u) v[u] = w[u];
+            }
+          }
+          for (; tl0 < nt; ++tl0) {              // the last frames of an utterance
+            cached = __fadd_rn(cached, dd[tl0 * st]);
+            ds[tl0 * st] = cached;
+          }
+        } else {                                 // some difference of the tile is inexact: as written, in fp64
+          const float *xg = x + (int64_t)t0 * mel + tid;
           for (int tl = 0; tl < nt; ++tl) {
-            const float xv = dx[tl * mel];
+            const float xv = xg[(int64_t)tl * mel];
             if (tb + t0 + tl >= kCmvnWindow) {
-              const float xo = dxo[tl * mel];
-              const float dh = __fsub_rn(xv, xo);                      // TwoSum(x, -x_old)
-              const float bv = __fsub_rn(dh, xv);
-              const float dl = __fadd_rn(__fsub_rn(xv, __fsub_rn(dh, bv)), __fsub_rn(-xo, bv));
-              if (dl == 0.0f) {
-                cached = __fadd_rn(cached, dh);
-              } else {                                                 // inexact difference: as written
-                double s2 = (double)cached;
-                s2 += (double)xv;
-                s2 += -1.0 * (double)xo;
-                cached = (float)s2;
-              }
+              const float xo = xg[((int64_t)tl - kCmvnWindow) * mel];
+              double s2 = (double)cached;
+              s2 += (double)xv;
+              s2 += -1.0 * (double)xo;
+              cached = (float)s2;
             } else {
               cached = __fadd_rn(cached, xv);
             }
-            ds[tl * mel] = cached;
+            ds[tl * nb] = cached;
           }
         }
       }
     } else {
       if (j + 1 < n_tiles) fetch_tile(j + 1);    // in flight during the stores below
       if (j > 0) store_tile(j - 1);              // reads buffers (j-1)&1 ...
+      if (wtid == 0) inexact[(j + 1) & 1] = 0;   // (the chain read that flag one iteration ago)
       asm volatile("bar.sync 1, %0;" ::"r"(n_workers) : "memory");
       if (j + 1 < n_tiles) commit_tile(j + 1);   // ... which tile j+1 then overwrites
     }
     __syncthreads();
   }
   if (!is_chain) store_tile(n_tiles - 1);
-  if (state && is_chain && tid < mel) state[(int64_t)blockIdx.x * mel + tid] = cached;
+  if (state && is_chain && tid < nb) state[(int64_t)blockIdx.x * mel + b0 + tid] = cached;
   if (minmax && !is_chain) {                     // the utterance's min/max for the first Quantize
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -286,23 +324,41 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
     SetError("CmvnLaunch: num_mel %d > %d", num_mel, kMaxMel);
     return CE_GPU_EINVAL;
   }
+  // Bins per CTA: all of them when there are utterances enough to fill the GPU; groups of 8 (one 32-byte
+  // sector of every frame) for a few long ones -- the bins' chains are independent, and a CTA with fewer
+  // bins affords longer tiles (fewer barriers per frame).
+  int64_t total_frames = 0;
+  for (int u = 0; u < n_utts; ++u) total_frames += h[u].T;
+  const bool split = global_stats_dev && num_mel % 8 == 0 && n_utts < 64 && total_frames / std::max(1, n_utts) >= 4096;
+  static const int nb_env = getenv("CE_GPU_CMVN_BINS") ? atoi(getenv("CE_GPU_CMVN_BINS")) : 0;   // A/B: bins per CTA
+  const int nb_per = (nb_env > 0 && num_mel % nb_env == 0) ? nb_env : split ? (n_utts < 4 ? 4 : 8) : num_mel;
+  const int n_groups = (num_mel + nb_per - 1) / nb_per;
   // frames per tile: the largest power of two whose tile the worker threads cover with 16 elements each
-  const int workers = kCmvnThreads - (global_stats_dev ? (num_mel + 31) / 32 * 32 : 0);
-  int tile_frames = 64;
-  while (tile_frames > 1 && tile_frames * num_mel > 16 * workers) tile_frames >>= 1;
-  const size_t smem = sizeof(float) * 6 * (size_t)tile_frames * num_mel;
+  const int workers = kCmvnThreads - (global_stats_dev ? (nb_per + 31) / 32 * 32 : 0);
+  int tile_frames = 512;
+  while (tile_frames > 1 && tile_frames * nb_per > 16 * workers) tile_frames >>= 1;
+  const size_t smem = sizeof(float) * 6 * (size_t)tile_frames * nb_per + 16;
   static thread_local size_t configured[64] = {0};
   int dev = 0;
   CE_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || smem > configured[dev]) {
-    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev < 64) configured[dev] = smem;
   }
   ProfScope prof(kProfCmvn, s);
-  cmvn_kernel<<<(unsigned)n_utts, kCmvnThreads, smem, s>>>(global_stats_dev, steps, feats_dev,
-                                                           utts->dev<CmvnUtt>(), n_utts, num_mel,
-                                                           tile_frames, pad_left, pad_right, out_dev,
-                                                           out_stride, resume ? resume->state_dev : nullptr, minmax_dev);
+#define CE_CMVN_LAUNCH(NBT)                                                                                   \
+  cmvn_kernel<NBT><<<dim3((unsigned)n_utts, (unsigned)n_groups), kCmvnThreads, smem, s>>>(                     \
+      global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(), n_utts, num_mel, nb_per, tile_frames, pad_left, \
+      pad_right, out_dev, out_stride, resume ? resume->state_dev : nullptr, minmax_dev)
+  const bool whole = num_mel % nb_per == 0;      // every CTA has exactly nb_per bins
+  if (whole && nb_per == 40) CE_CMVN_LAUNCH(40);
+  else if (whole && nb_per == 8) CE_CMVN_LAUNCH(8);
+  else if (whole && nb_per == 4) CE_CMVN_LAUNCH(4);
+  else CE_CMVN_LAUNCH(0);
+#undef CE_CMVN_LAUNCH
   CE_LAUNCHED();
   HostMark("cmvn: launch");
   return CE_GPU_OK;

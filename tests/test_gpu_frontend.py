@@ -165,6 +165,33 @@ def test_cmvn_chain_exact_on_adversarial_values(port, golden):
     assert np.array_equal(out, port.cmvn(golden["cmvn_stats"], feats))
 
 
+def test_cmvn_long_utterances_bins_over_several_ctas(port, golden):
+    """A few long utterances: the kernel gives every CTA a group of 4 (fewer than 4 utterances) or 8 bins and
+    long tiles; the workers make x_t - x_{t-600} and its exactness test, one inexact element sends its whole
+    tile through the fp64 form.  Bit-identical to the in-order chain of src/cmvn.cc:42-67 either way."""
+    rng = np.random.default_rng(31)
+    stats = golden["cmvn_stats"]
+    # (a) log-mel-like values in one binade pair: every difference exact, the fast path all the way
+    feats = rng.uniform(9.0, 26.0, size=(9000, 40)).astype(np.float32)
+    feats = np.round(feats * 64.0) / 64.0                # coarse mantissas: exact differences
+    out = api.cmvn(stats, feats.astype(np.float32))
+    assert np.array_equal(out, port.cmvn(stats, feats.astype(np.float32)))
+    # (b) full-mantissa values: inexact differences in most tiles (the fp64 form), 6 utterances -> groups of 8
+    sizes = [4500, 4100, 5000, 4096, 4200, 6000]
+    feats = (13.0 + 4.0 * rng.standard_normal((sum(sizes), 40))).astype(np.float32)
+    feats[rng.random(feats.shape) < 0.02] *= 1e-3        # a few small values: certainly inexact against 13
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    out = api.cmvn(stats, feats, off)
+    for u in range(len(sizes)):
+        assert np.array_equal(out[off[u]:off[u + 1]], port.cmvn(stats, feats[off[u]:off[u + 1]])), u
+    # (c) one long utterance, mostly exact with isolated inexact elements (mixed fast / fp64 tiles), groups of 4
+    feats = (np.round(rng.uniform(9.0, 26.0, size=(7000, 40)) * 64.0) / 64.0).astype(np.float32)
+    for t in (650, 1999, 2000, 5555):
+        feats[t, rng.integers(0, 40)] = np.float32(1e-3) * np.float32(rng.uniform(1, 2))
+    out = api.cmvn(stats, feats)
+    assert np.array_equal(out, port.cmvn(stats, feats))
+
+
 def test_cmvn_in_place_on_device(golden, port):
     import torch
     rng = np.random.default_rng(12)
