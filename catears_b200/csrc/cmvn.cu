@@ -52,8 +52,12 @@ constexpr int kCmvnThreads = 256;
 // several SMs and its tiles get long: the chain of a bin is sequential, its bins are not).
 // Shared memory: x[2][TF][nb], d[2][TF][nb] (x_t - x_{t-600}), S[2][TF][nb] floats, then inexact[2].
 // NBT: nb_per as a compile-time constant (the chain's loads and stores then take immediate offsets), 0 = any.
-template <int NBT>
-__global__ void __launch_bounds__(kCmvnThreads)
+// CHAIN_DIFF: who makes d = x_t - x_{t-600} and its exactness test.  false: the workers, while they stage the
+// tile (a few long utterances: the chain is the bound and does nothing but add); true: the chain threads, eight
+// frames at a time ahead of the dependent adds (a batch of many utterances: there the workers are the bound --
+// the test costs them a fifth more instructions -- and the chain has time to spare).
+template <int NBT, bool CHAIN_DIFF>
+__global__ void __launch_bounds__(kCmvnThreads, 2)
 cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
             const float *__restrict__ feats, const CmvnUtt *__restrict__ utts, int n_utts,
             int mel, int nb_per, int tile_frames, int pad_left, int pad_right, float *__restrict__ out,
@@ -118,6 +122,17 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
     float *dx = xs + (j & 1) * tile_elems;
     float *dd = dds + (j & 1) * tile_elems;
     bool bad = false;
+    if (CHAIN_DIFF) {
+#pragma unroll
+      for (int k = 0; k < kPerThread; ++k) {
+        const int i = wtid + k * n_workers;
+        if (i < n) {
+          dx[i] = la[k];
+          dd[i] = lb[k];                         // x_{t-600} itself (0 for t < 600)
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
       const int i = wtid + k * n_workers;
@@ -176,7 +191,51 @@ cmvn_kernel(const float *__restrict__ g, const CmvnStep *__restrict__ steps,
         const int nt = min(TF, T - t0);
         const float *dd = dds + (j & 1) * tile_elems + tid;
         float *ds = ss + (j & 1) * tile_elems + tid;
-        if (!inexact[j & 1]) {                   // (always, for log-mel features)
+        if (CHAIN_DIFF) {
+          const int st = NBT ? NBT : nb;
+          const float *px = xs + (j & 1) * tile_elems + tid;
+          constexpr int kB = 8;
+          for (int tl0 = 0; tl0 < nt; tl0 += kB) {
+            float a[kB], o[kB], dh[kB];
+            bool bad = false;
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {
+              const bool in = tl0 + u < nt;
+              a[u] = in ? px[(tl0 + u) * st] : 0.0f;
+              o[u] = in ? dd[(tl0 + u) * st] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {                             // TwoSum(x, -x_old), off the chain
+              dh[u] = __fsub_rn(a[u], o[u]);
+              const float bv = __fsub_rn(dh[u], a[u]);
+              const float dl = __fadd_rn(__fsub_rn(a[u], __fsub_rn(dh[u], bv)), __fsub_rn(-o[u], bv));
+              bad |= dl != 0.0f;
+            }
+            if (!bad) {
+#pragma unroll
+              for (int u = 0; u < kB; ++u) {
+                if (tl0 + u < nt) {
+                  cached = __fadd_rn(cached, dh[u]);
+                  ds[(tl0 + u) * st] = cached;
+                }
+              }
+            } else {                             // an inexact difference among these frames: as written, in fp64
+              for (int u = 0; u < kB; ++u) {
+                if (tl0 + u < nt) {
+                  if (tb + t0 + tl0 + u >= kCmvnWindow) {
+                    double s2 = (double)cached;
+                    s2 += (double)a[u];
+                    s2 += -1.0 * (double)o[u];
+                    cached = (float)s2;
+                  } else {
+                    cached = __fadd_rn(cached, a[u]);
+                  }
+                  ds[(tl0 + u) * st] = cached;
+                }
+              }
+            }
+          }
+        } else if (!inexact[j & 1]) {            // (always, for log-mel features)
           // 16 differences are in registers before the first sum is stored, and the next 16 are on their
           // way while these are added: as a plain loop every load waited behind the store before it (the
           // compiler must assume they alias) and a frame cost ~140 clocks; only the add is sequential.
@@ -342,22 +401,22 @@ int CmvnLaunch(const float *global_stats_dev, float global_count, const float *f
   int dev = 0;
   CE_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || smem > configured[dev]) {
-    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CE_CUDA(cudaFuncSetAttribute(cmvn_kernel<40, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev < 64) configured[dev] = smem;
   }
   ProfScope prof(kProfCmvn, s);
-#define CE_CMVN_LAUNCH(NBT)                                                                                   \
-  cmvn_kernel<NBT><<<dim3((unsigned)n_utts, (unsigned)n_groups), kCmvnThreads, smem, s>>>(                     \
+#define CE_CMVN_LAUNCH(NBT, CD)                                                                               \
+  cmvn_kernel<NBT, CD><<<dim3((unsigned)n_utts, (unsigned)n_groups), kCmvnThreads, smem, s>>>(                 \
       global_stats_dev, steps, feats_dev, utts->dev<CmvnUtt>(), n_utts, num_mel, nb_per, tile_frames, pad_left, \
       pad_right, out_dev, out_stride, resume ? resume->state_dev : nullptr, minmax_dev)
   const bool whole = num_mel % nb_per == 0;      // every CTA has exactly nb_per bins
-  if (whole && nb_per == 40) CE_CMVN_LAUNCH(40);
-  else if (whole && nb_per == 8) CE_CMVN_LAUNCH(8);
-  else if (whole && nb_per == 4) CE_CMVN_LAUNCH(4);
-  else CE_CMVN_LAUNCH(0);
+  if (whole && nb_per == 40) CE_CMVN_LAUNCH(40, true);
+  else if (whole && nb_per == 8) CE_CMVN_LAUNCH(8, false);
+  else if (whole && nb_per == 4) CE_CMVN_LAUNCH(4, false);
+  else CE_CMVN_LAUNCH(0, true);
 #undef CE_CMVN_LAUNCH
   CE_LAUNCHED();
   HostMark("cmvn: launch");
