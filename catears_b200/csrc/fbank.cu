@@ -273,7 +273,9 @@ fbank_kernel(const int16_t *__restrict__ pcm, int64_t total_samples,
   }
   for (int i = tid; i < kFrameLen; i += kThreads) s_ham[i] = tab->hamming[i];
   for (int i = tid; i < tab->n_weights; i += kThreads) s_w[i] = tab->weights[i];
-  for (int i = tid; i < 256; i += kThreads) s_tw[(i & 15) * 16 + (i >> 4)] = tab->tw256[i];   // [n1][k2] -> [k2][n1]
+  // [n1][k2] -> [k2][n1]: the transposing side is the (cached, 2 KB) global read; written the other way round
+  // every warp's store hit one bank pair 16 times over (ncu: 4 % of the kernel's shared-memory wavefronts)
+  for (int i = tid; i < 256; i += kThreads) s_tw[i] = tab->tw256[(i & 15) * 16 + (i >> 4)];
   __syncthreads();
 
   // ---- phase 1b: d[s] = x[s] - 0.97 x[s-1]; exact sums of 80-sample blocks ----
