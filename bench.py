@@ -710,10 +710,11 @@ def run_longform(args):
     minute = synth.synth_utterance(7, 16000 * 60, seed=7)
     pcm = np.tile(minute, 60)
     total = int(api.frame_offsets([0, pcm.size])[-1])
-    # Shards of ~4096 kept frames, a contiguous run of them per GPU, evaluated as ONE batch per GPU:
-    # the online CMVN is a sequential chain per utterance, so one 45 000-frame shard per GPU would
-    # serialise on a single CTA; ~90 shards cost 15 % halo recomputation and run like a batch.
-    n_shards = max(world, (total + 4095) // 4096)
+    # Shards of --shard-frames kept frames, a contiguous run of them per GPU, evaluated as ONE batch per GPU.
+    # (Round 1 needed ~90 shards of 4096 frames -- 15 % halo recomputation -- because the online CMVN chain
+    # of a 45 000-frame shard took 5 ms on its single CTA; the chain now costs 16 clocks a frame and a long
+    # utterance's bins spread over several CTAs: 16 384-frame shards measure best, 358 k x against 326 k x.)
+    n_shards = max(world, (total + args.shard_frames - 1) // args.shard_frames)
     if args.exact:
         # --exact: the hour as ONE utterance -- the online CMVN chain runs from the first frame (bit-identical to
         # the reference's frame-by-frame evaluation of the whole stream: no warm-up halo, no fp32-rounding
@@ -894,6 +895,8 @@ def main():
     ap.add_argument("--feed", default="none", choices=["none", "topk"],
                     help="longform: rows to pinned host memory + a pool of consumer threads (config 5's decoder feed)")
     ap.add_argument("--feed-topk", type=int, default=64)
+    ap.add_argument("--shard-frames", type=int, default=16384,
+                    help="longform: kept frames per time shard (each shard recomputes L + 600 + R halo frames)")
     ap.add_argument("--exact", action="store_true",
                     help="longform: the whole stream as one utterance (exact online CMVN, one GPU)")
     ap.add_argument("--feed-threads", type=int, default=8)
